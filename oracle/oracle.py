@@ -1,0 +1,559 @@
+"""CPU ORACLE driver (test infrastructure, NOT product code).
+
+Restates the reference's host-side photomosaic path in Python on top of
+  * cv2 (OpenCV, the reference's own third-party dependency; reference pins 4.5.2 in
+    Shared.props:5, this image has 4.13) for every OpenCV call the reference makes, and
+  * oracle/_ref/libmosaic_oracle.so (mosaic_oracle.c) for the f64 per-pixel loops.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module. The product (mosaicmagnifique_b200) never does.
+
+Reference citations (all under /root/reference/src):
+  CellShape.resized            CellShape/CellShape.cpp:281-312, setCellMask :116-135
+  CellGroup detail/size steps  CellShape/CellGroup.cpp:65-128
+  resizeImage / batchResize    Other/ImageUtility.cpp:34-101
+  preprocessMainImage          Photomosaic/PhotomosaicGeneratorBase.cpp:223-252
+  preprocessLibraryImages      Photomosaic/PhotomosaicGeneratorBase.cpp:255-290
+  getCellAt                    Photomosaic/PhotomosaicGeneratorBase.cpp:293-329
+  generateBestFits             Photomosaic/CPUPhotomosaicGenerator.cpp:33-112
+  ColourScheme variants        Photomosaic/ColourScheme.cpp:36-177
+  getGridState / findCellState Grid/GridGenerator.cpp:29-193
+  mergeBounds                  Grid/GridBounds.cpp:39-104
+  .mcs container               CellShape/CellShape.cpp:363-434, Other/CustomQDataStream.h:56-87
+
+Parity pinning: the colour maths is pinned by the reference's 48 known-answer vectors and by
+the reference's own ColourDifference.cpp / GridUtility.cpp compiled unmodified (libref_core.so).
+The OpenCV numerics (Lab LUT, INTER_AREA, HSV) have no golden vectors in the reference
+("parity unpinned" for those); cv2 itself is used here, so the oracle is OpenCV by construction.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import struct
+import subprocess
+from dataclasses import dataclass, field, replace
+
+import numpy as np
+
+try:  # cv2 is only needed for preprocessing; the C core works without it
+    import cv2
+except Exception:  # pragma: no cover
+    cv2 = None
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PAD_GRID = 2  # Grid/GridUtility.h:33
+RGB_EUCLIDEAN, CIE76, CIEDE2000 = 0, 1, 2  # Photomosaic/ColourDifference.h:13-19
+# Photomosaic/ColourScheme.h:10-19
+SCHEME_NONE, SCHEME_COMPLEMENTARY, SCHEME_TRIADIC, SCHEME_COMPOUND, SCHEME_TETRADIC, SCHEME_ANALAGOUS = range(6)
+SCHEME_ROTATIONS = {0: (), 1: (180.0,), 2: (120.0, 240.0), 3: (150.0, 210.0), 4: (90.0, 180.0, 270.0),
+                    5: (30.0, 60.0, 90.0)}
+MAX_ENTROPY = 8.0  # Other/ImageUtility.h (log2(256))
+
+
+def build(force: bool = False) -> None:
+    """Compiles oracle/_ref/*.so with the committed Makefile (reference sources only if present)."""
+    out = os.path.join(HERE, "_ref", "libmosaic_oracle.so")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(os.path.join(HERE, "mosaic_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", HERE, "all"])
+
+
+_lib = None
+
+
+class _Shape(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in (
+        "size", "row_spacing", "col_spacing", "alt_row_spacing", "alt_col_spacing", "alt_row_offset",
+        "alt_col_offset", "alt_col_flip_h", "alt_col_flip_v", "alt_row_flip_h", "alt_row_flip_v")]
+
+
+class _Stats(ctypes.Structure):
+    _fields_ = [("visited", ctypes.c_int64), ("nominal", ctypes.c_int64)]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(os.path.join(HERE, "_ref", "libmosaic_oracle.so"))
+        dp, ip, fp, u8p, i64p = (ctypes.POINTER(t) for t in (ctypes.c_double, ctypes.c_int, ctypes.c_float,
+                                                              ctypes.c_uint8, ctypes.c_int64))
+        L.mo_rgb_euclidean.restype = ctypes.c_double
+        L.mo_rgb_euclidean.argtypes = [dp, dp]
+        L.mo_ciede2000.restype = ctypes.c_double
+        L.mo_ciede2000.argtypes = [dp, dp]
+        L.mo_diff_batch.argtypes = [ctypes.c_int, fp, fp, ctypes.c_int64, dp]
+        L.mo_grid_size.argtypes = [ctypes.POINTER(_Shape), ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ip]
+        L.mo_rect_at.argtypes = [ctypes.POINTER(_Shape), ctypes.c_int, ctypes.c_int, ip]
+        L.mo_flip_at.restype = ctypes.c_int
+        L.mo_flip_at.argtypes = [ctypes.POINTER(_Shape), ctypes.c_int, ctypes.c_int]
+        L.mo_cell_bounds.argtypes = [ctypes.POINTER(_Shape), ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_int, ip, ip, ip]
+        L.mo_calculate_repeats.restype = ctypes.c_int
+        L.mo_calculate_repeats.argtypes = [i64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, i64p, i64p]
+        L.mo_generate_step.restype = ctypes.c_int
+        L.mo_generate_step.argtypes = [ctypes.c_int, fp, ip, ip, ctypes.c_int, fp, ctypes.c_int64, ctypes.c_int, u8p,
+                                       i64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, dp, dp, ctypes.POINTER(_Stats)]
+        L.mo_select_from_D.argtypes = [dp, ctypes.c_int64, i64p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.mo_entropy.restype = ctypes.c_double
+        L.mo_entropy.argtypes = [u8p, u8p, ctypes.c_int64]
+        _lib = L
+    return _lib
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+# ----------------------------------------------------------------------------- colour maths
+
+def rgb_euclidean(a, b) -> float:
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return lib().mo_rgb_euclidean(_ptr(a, ctypes.c_double), _ptr(b, ctypes.c_double))
+
+
+cie76 = rgb_euclidean  # ColourDifference.h:41
+
+
+def ciede2000(a, b) -> float:
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return lib().mo_ciede2000(_ptr(a, ctypes.c_double), _ptr(b, ctypes.c_double))
+
+
+def diff_batch(diff_type: int, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float32).reshape(-1, 3)
+    b = np.ascontiguousarray(b, np.float32).reshape(-1, 3)
+    out = np.empty(a.shape[0], np.float64)
+    lib().mo_diff_batch(diff_type, _ptr(a, ctypes.c_float), _ptr(b, ctypes.c_float), a.shape[0], _ptr(out, ctypes.c_double))
+    return out
+
+
+# ----------------------------------------------------------------------------- cell shapes
+
+def resize_image_exact(img: np.ndarray, th: int, tw: int) -> np.ndarray:
+    """ImageUtility::resizeImage with ResizeType::EXACT (ImageUtility.cpp:34-62)."""
+    factor = th / img.shape[0]
+    if factor == 1.0:
+        factor = tw / img.shape[1]
+    if factor == 1.0:
+        return img
+    flags = cv2.INTER_AREA if factor < 1 else cv2.INTER_CUBIC
+    return cv2.resize(img, (tw, th), interpolation=flags)
+
+
+@dataclass
+class CellShape:
+    """CellShape (CellShape/CellShape.h:98-109): binary mask + tiling parameters."""
+    mask: np.ndarray  # size x size u8, 0/255
+    row_spacing: int = 0
+    col_spacing: int = 0
+    alt_row_spacing: int = 0
+    alt_col_spacing: int = 0
+    alt_row_offset: int = 0
+    alt_col_offset: int = 0
+    alt_col_flip_h: bool = False
+    alt_col_flip_v: bool = False
+    alt_row_flip_h: bool = False
+    alt_row_flip_v: bool = False
+    name: str = ""
+
+    @staticmethod
+    def from_mask(mask: np.ndarray) -> "CellShape":
+        """CellShape(const cv::Mat&) (CellShape.cpp:37-45) + setCellMask (:116-135)."""
+        m = np.where(np.asarray(mask, np.uint8) > 127, 255, 0).astype(np.uint8)  # THRESH_BINARY 127
+        assert m.shape[0] == m.shape[1], "non-square masks (imageToSquare PAD) are outside the oracle"
+        s = m.shape[0]
+        return CellShape(m, s, s, s, s)
+
+    @staticmethod
+    def square(size: int) -> "CellShape":
+        """CellShape(size_t) default cell (CellShape.cpp:66-69)."""
+        return CellShape.from_mask(np.full((size, size), 255, np.uint8))
+
+    @property
+    def size(self) -> int:
+        return self.mask.shape[0]
+
+    def flipped(self, h: bool, v: bool) -> np.ndarray:
+        m = self.mask
+        if h:
+            m = m[:, ::-1]
+        if v:
+            m = m[::-1, :]
+        return np.ascontiguousarray(m)
+
+    def masks4(self) -> np.ndarray:
+        """index = flip_h + 2*flip_v (CellGroup.cpp:146 order)."""
+        return np.stack([self.flipped(False, False), self.flipped(True, False), self.flipped(False, True),
+                         self.flipped(True, True)])
+
+    def resized(self, size: int) -> "CellShape":
+        """CellShape::resized (CellShape.cpp:281-312)."""
+        if self.mask.size == 0 or size == self.size:
+            return replace(self)
+        rm = resize_image_exact(self.mask, size, size)
+        out = CellShape.from_mask(rm)
+        ratio = rm.shape[0] / self.mask.shape[0]
+        fl = lambda v: int(np.floor(v * ratio))
+        out.row_spacing = max(fl(self.row_spacing), 1)
+        out.col_spacing = max(fl(self.col_spacing), 1)
+        out.alt_row_spacing = max(fl(self.alt_row_spacing), 1)
+        out.alt_col_spacing = max(fl(self.alt_col_spacing), 1)
+        out.alt_row_offset = fl(self.alt_row_offset)
+        out.alt_col_offset = fl(self.alt_col_offset)
+        out.alt_col_flip_h, out.alt_col_flip_v = self.alt_col_flip_h, self.alt_col_flip_v
+        out.alt_row_flip_h, out.alt_row_flip_v = self.alt_row_flip_h, self.alt_row_flip_v
+        out.name = self.name
+        return out
+
+    def c_shape(self) -> _Shape:
+        return _Shape(self.size, self.row_spacing, self.col_spacing, self.alt_row_spacing, self.alt_col_spacing,
+                      self.alt_row_offset, self.alt_col_offset, int(self.alt_col_flip_h), int(self.alt_col_flip_v),
+                      int(self.alt_row_flip_h), int(self.alt_row_flip_v))
+
+    def params(self) -> list:
+        c = self.c_shape()
+        return [getattr(c, n) for n, _ in _Shape._fields_]
+
+
+def load_mcs(path: str) -> CellShape:
+    """.mcs v8 reader (CellShape.cpp:363-434; QDataStream big-endian, CustomQDataStream.h:56-87)."""
+    d = open(path, "rb").read()
+    o = 0
+
+    def u32():
+        nonlocal o
+        v = struct.unpack_from(">I", d, o)[0]; o += 4
+        return v
+
+    def i32():
+        nonlocal o
+        v = struct.unpack_from(">i", d, o)[0]; o += 4
+        return v
+
+    magic, version = u32(), u32()
+    if magic != 0x87AECFB1:
+        raise ValueError("not a .mcs file")
+    n = u32()
+    name = "" if n == 0xFFFFFFFF else d[o:o + n].decode("utf-16-be"); o += 0 if n == 0xFFFFFFFF else n
+    n = u32()
+    png = d[o:o + n]; o += n
+    mask = cv2.imdecode(np.frombuffer(png, np.uint8), cv2.IMREAD_UNCHANGED)
+    if mask.ndim == 3:
+        mask = mask[..., 0]
+    rs, cs, ars, acs, aro, aco = (i32() for _ in range(6))
+    fl = struct.unpack_from(">4?", d, o)
+    shape = CellShape.from_mask(mask)
+    shape.row_spacing, shape.col_spacing, shape.alt_row_spacing, shape.alt_col_spacing = rs, cs, ars, acs
+    shape.alt_row_offset, shape.alt_col_offset = aro, aco
+    shape.alt_col_flip_h, shape.alt_col_flip_v, shape.alt_row_flip_h, shape.alt_row_flip_v = fl
+    shape.name = name
+    shape._version = version
+    return shape
+
+
+@dataclass
+class CellGroup:
+    """CellGroup (CellShape/CellGroup.cpp:29-128): per size step a normal and a detail cell."""
+    cells: list = field(default_factory=list)
+    detail_cells: list = field(default_factory=list)
+    detail: float = 1.0
+    size_steps: int = 0
+
+    @staticmethod
+    def make(shape: CellShape, detail_percent: int = 100, size_steps: int = 0) -> "CellGroup":
+        g = CellGroup()
+        g.detail = detail_percent / 100.0
+        g.size_steps = size_steps
+        g.cells = [shape]
+        g.detail_cells = [shape.resized(max(int(shape.size * g.detail), 1))]  # CellGroup.cpp:79-80
+        size = shape.size
+        for _ in range(size_steps):
+            size //= 2  # CellGroup.cpp:105
+            g.cells.append(g.cells[-1].resized(size))
+            g.detail_cells.append(g.cells[-1].resized(max(int(size * g.detail), 1)))  # :114
+        return g
+
+
+# ----------------------------------------------------------------------------- grid geometry
+
+def grid_size(shape: CellShape, w: int, h: int, pad: int = PAD_GRID):
+    gx, gy = ctypes.c_int(), ctypes.c_int()
+    s = shape.c_shape()
+    lib().mo_grid_size(ctypes.byref(s), w, h, pad, ctypes.byref(gx), ctypes.byref(gy))
+    return gx.value, gy.value
+
+
+def rect_at(shape: CellShape, x: int, y: int):
+    r = (ctypes.c_int * 4)()
+    s = shape.c_shape()
+    lib().mo_rect_at(ctypes.byref(s), x, y, r)
+    return tuple(r)
+
+
+def flip_at(shape: CellShape, x: int, y: int) -> int:
+    s = shape.c_shape()
+    return lib().mo_flip_at(ctypes.byref(s), x, y)
+
+
+def cell_bounds(normal: CellShape, detail_size: int, detail: float, x: int, y: int, w: int, h: int):
+    g, l, d = (ctypes.c_int * 4)(), (ctypes.c_int * 4)(), (ctypes.c_int * 4)()
+    s = normal.c_shape()
+    lib().mo_cell_bounds(ctypes.byref(s), detail_size, detail, x, y, w, h, g, l, d)
+    return tuple(g), tuple(l), tuple(d)
+
+
+# ----------------------------------------------------------------------------- grid state (GridGenerator)
+
+def _merge_bounds(bounds: list) -> list:
+    """GridBounds::mergeBounds (GridBounds.cpp:39-104); rects are [x, y, w, h]."""
+    def union(a, b):
+        x0, y0 = min(a[0], b[0]), min(a[1], b[1])
+        x1, y1 = max(a[0] + a[2], b[0] + b[2]), max(a[1] + a[3], b[1] + b[3])
+        return [x0, y0, x1 - x0, y1 - y0]
+
+    bounds = [list(b) for b in bounds]
+    merged_any = True
+    while merged_any:
+        merged_any = False
+        i = 0
+        while i + 1 < len(bounds):
+            j = i + 1
+            while j < len(bounds) and i + 1 < len(bounds):
+                a, b = bounds[i], bounds[j]
+                merge = False
+                if a[0] == b[0] and a[2] == b[2]:
+                    yd = b[1] - a[1]
+                    merge = yd == 0 or (0 < yd <= a[3]) or (yd < 0 and -yd <= b[3])
+                elif a[1] == b[1] and a[3] == b[3]:
+                    xd = b[0] - a[0]
+                    merge = xd == 0 or (0 < xd <= a[2]) or (xd < 0 and -xd <= b[2])
+                else:
+                    u = union(a, b)
+                    merge = u == a or u == b
+                if merge:
+                    bounds[i] = union(a, b)
+                    del bounds[j]
+                    merged_any = True
+                else:
+                    j += 1
+            if i + 1 < len(bounds):
+                i += 1
+            else:
+                break
+    return bounds
+
+
+def entropy(gray: np.ndarray, mask: np.ndarray | None) -> float:
+    gray = np.ascontiguousarray(gray, np.uint8)
+    m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+    return lib().mo_entropy(_ptr(gray, ctypes.c_uint8), None if m is None else _ptr(m, ctypes.c_uint8), gray.size)
+
+
+def grid_state(group: CellGroup, main_bgr: np.ndarray | None, height: int = 0, width: int = 0) -> list:
+    """GridGenerator::getGridState (GridGenerator.cpp:29-110). Returns one int64 array per generated step,
+    -1 = nullopt, 0 = valid."""
+    gh = height if main_bgr is None else main_bgr.shape[0]
+    gw = width if main_bgr is None else main_bgr.shape[1]
+    active = [[0, 0, gw, gh]]
+    out = []
+    clamp = lambda v, lo, hi: max(lo, min(v, hi))
+    for step in range(group.size_steps + 1):
+        if not active:
+            break
+        shape = group.cells[step]
+        dshape = group.detail_cells[step]
+        dmasks = dshape.masks4()
+        gx, gy = grid_size(shape, gw, gh)
+        g = np.full((gy, gx), -1, np.int64)
+        nxt = []
+        for y in range(-PAD_GRID, gy - PAD_GRID):
+            for x in range(-PAD_GRID, gx - PAD_GRID):
+                r = rect_at(shape, x, y)
+                # findCellState (GridGenerator.cpp:113-193)
+                inb = False
+                for b in active:
+                    y0, y1 = clamp(r[1], b[1], b[1] + b[3]), clamp(r[1] + r[3], b[1], b[1] + b[3])
+                    x0, x1 = clamp(r[0], b[0], b[0] + b[2]), clamp(r[0] + r[2], b[0], b[0] + b[2])
+                    if y0 != y1 and x0 != x1:
+                        inb = True
+                        break
+                if not inb:
+                    continue
+                split = False
+                if main_bgr is not None and step < group.size_steps:
+                    _, local, db = cell_bounds(shape, dshape.size, group.detail, x, y, gw, gh)
+                    y0, y1 = clamp(r[1], 0, gh), clamp(r[1] + r[3], 0, gh)
+                    x0, x1 = clamp(r[0], 0, gw), clamp(r[0] + r[2], 0, gw)
+                    cell = main_bgr[y0:y1, x0:x1]
+                    mask = dmasks[flip_at(shape, x, y)][db[1]:db[1] + db[3], db[0]:db[0] + db[2]]
+                    if cell.size:
+                        cell = resize_image_exact(np.ascontiguousarray(cell), mask.shape[0], mask.shape[1])
+                        gray = cv2.cvtColor(cell, cv2.COLOR_BGR2GRAY)
+                        split = entropy(gray, np.ascontiguousarray(mask)) >= MAX_ENTROPY * 0.7
+                    # an empty cell has entropy 0 (ImageUtility.cpp:191-192)
+                if split:
+                    y0, y1 = clamp(r[1], 0, gh), clamp(r[1] + r[3], 0, gh)
+                    x0, x1 = clamp(r[0], 0, gw), clamp(r[0] + r[2], 0, gw)
+                    if y0 != y1 and x0 != x1:
+                        nxt.append([x0, y0, x1 - x0, y1 - y0])
+                else:
+                    g[y + PAD_GRID, x + PAD_GRID] = 0
+        out.append(g)
+        active = _merge_bounds(nxt) if nxt else []
+    return out
+
+
+# ----------------------------------------------------------------------------- preprocessing
+
+def colour_scheme_variants(img_bgr8: np.ndarray, scheme: int) -> list:
+    """ColourScheme::getColourScheme* (ColourScheme.cpp:36-177): original + hue-rotated 8U copies."""
+    out = [img_bgr8]
+    rots = SCHEME_ROTATIONS[scheme]
+    if not rots:
+        return out
+    hsv = cv2.cvtColor(img_bgr8.astype(np.float32), cv2.COLOR_BGR2HSV_FULL)
+    for r in rots:
+        h = hsv.copy()
+        h[..., 0] = np.fmod(h[..., 0] + np.float32(r), np.float32(360.0))
+        bgr = cv2.cvtColor(h, cv2.COLOR_HSV2BGR_FULL)
+        out.append(np.clip(np.rint(bgr), 0, 255).astype(np.uint8))  # convertTo(8U) = saturate_cast(cvRound)
+    return out
+
+
+def to_working_space(img_bgr8: np.ndarray, diff_type: int) -> np.ndarray:
+    """PhotomosaicGeneratorBase.cpp:238-247 / :274-286."""
+    if diff_type in (CIE76, CIEDE2000):
+        f = img_bgr8.astype(np.float32) * np.float32(1 / 255.0)  # convertTo(CV_32F, 1/255.0): f32 multiply
+        return cv2.cvtColor(f, cv2.COLOR_BGR2Lab)
+    return img_bgr8.astype(np.float32)
+
+
+def preprocess_library(lib_bgr8: np.ndarray, group: CellGroup, diff_type: int) -> np.ndarray:
+    """preprocessLibraryImages (PhotomosaicGeneratorBase.cpp:255-290). lib: N x S x S x 3 u8."""
+    size0 = int(round(group.detail_cells[0].size))
+    out = []
+    for im in lib_bgr8:
+        if group.detail != 1:
+            flags = cv2.INTER_AREA if group.detail < 1 else cv2.INTER_CUBIC
+            im = cv2.resize(im, (size0, size0), interpolation=flags)
+        out.append(to_working_space(np.ascontiguousarray(im), diff_type))
+    return np.stack(out)
+
+
+def halve_library(lib_f32: np.ndarray) -> np.ndarray:
+    """ImageUtility::batchResizeMat(lib, 0.5) (ImageUtility.cpp:91-101) applied per step
+    (CPUPhotomosaicGenerator.cpp:95-99)."""
+    s = int(round(0.5 * lib_f32.shape[1]))
+    return np.stack([resize_image_exact(im, s, s) for im in lib_f32])
+
+
+def extract_cells(mains_f32: list, group: CellGroup, step: int, grid: np.ndarray, shared_buffer_quirk: bool = True):
+    """getCellAt (PhotomosaicGeneratorBase.cpp:293-329) for every valid cell of one step, raster order.
+    Returns cells [n, V, ds, ds, 3] f32, bounds [n,4] (detail space x,y,w,h), flips [n], coords [n,2] (x,y unpadded).
+
+    shared_buffer_quirk reproduces Q1 of SURVEY.md: the V cell Mats share ONE buffer
+    (std::vector<cv::Mat>(n, cv::Mat(...)), :310) and resizeImage returns its input when the factor
+    is 1 (ImageUtility.cpp:47-48), so at detail 100 % every variant equals the LAST one."""
+    shape, dshape = group.cells[step], group.detail_cells[step]
+    H, W = mains_f32[0].shape[:2]
+    V = len(mains_f32)
+    cells, bounds, flips, coords = [], [], [], []
+    rows, cols = grid.shape
+    for gy in range(rows):
+        for gx in range(cols):
+            if grid[gy, gx] < 0:
+                continue
+            x, y = gx - PAD_GRID, gy - PAD_GRID
+            gcl, local, db = cell_bounds(shape, dshape.size, group.detail, x, y, W, H)
+            vs = []
+            shared = np.zeros((shape.size, shape.size, 3), np.float32)
+            for v in range(V):
+                buf = shared if shared_buffer_quirk else np.zeros((shape.size, shape.size, 3), np.float32)
+                if local[2] > 0 and local[3] > 0:
+                    buf[local[1]:local[1] + local[3], local[0]:local[0] + local[2]] = \
+                        mains_f32[v][gcl[1]:gcl[3], gcl[0]:gcl[2]]
+                vs.append(buf)
+            if dshape.size != shape.size:
+                # the shared buffer holds the last variant by the time the resizes run (:311-316)
+                vs = [resize_image_exact(b, dshape.size, dshape.size) for b in vs]
+            cells.append(np.stack(vs))
+            bounds.append(db)
+            flips.append(flip_at(shape, x, y))
+            coords.append((x, y))
+    n = len(cells)
+    ds = dshape.size
+    return (np.stack(cells) if n else np.zeros((0, V, ds, ds, 3), np.float32),
+            np.asarray(bounds, np.int32).reshape(n, 4), np.asarray(flips, np.int32), np.asarray(coords, np.int32).reshape(n, 2))
+
+
+# ----------------------------------------------------------------------------- generate
+
+@dataclass
+class StepResult:
+    grid: np.ndarray            # rows x cols int64, -1 = nullopt
+    D: np.ndarray | None        # n_valid x N f64: min over variants of the masked sums (no penalty)
+    margins: np.ndarray | None  # n_valid x 2: best and second-best penalised scores
+    n_valid: int
+    visited: int
+    nominal: int
+    coords: np.ndarray          # n_valid x 2 unpadded (x, y)
+
+
+def generate_step(diff_type, cells, bounds, flips, lib_f32, masks4, grid, repeat_range, repeat_addition,
+                  want_D=True, early_exit=True, y_begin=0, y_end=None) -> StepResult:
+    """One size step of CPUPhotomosaicGenerator::generateBestFits on preprocessed inputs."""
+    L = lib()
+    grid = np.ascontiguousarray(grid, np.int64).copy()
+    rows, cols = grid.shape
+    n_valid = int((grid >= 0).sum())
+    cells = np.ascontiguousarray(cells, np.float32)
+    V = cells.shape[1] if n_valid else 1
+    ds = masks4.shape[1]
+    lib_f32 = np.ascontiguousarray(lib_f32, np.float32)
+    N = lib_f32.shape[0]
+    bounds = np.ascontiguousarray(bounds, np.int32)
+    flips = np.ascontiguousarray(flips, np.int32)
+    masks4 = np.ascontiguousarray(masks4, np.uint8)
+    D = np.full((n_valid, N), np.nan, np.float64) if want_D else None
+    margins = np.full((n_valid, 2), np.nan, np.float64) if want_D else None
+    st = _Stats(0, 0)
+    rc = L.mo_generate_step(diff_type, _ptr(cells, ctypes.c_float), _ptr(bounds, ctypes.c_int), _ptr(flips, ctypes.c_int),
+                            V, _ptr(lib_f32, ctypes.c_float), N, ds, _ptr(masks4, ctypes.c_uint8),
+                            _ptr(grid, ctypes.c_int64), rows, cols, repeat_range, repeat_addition, int(early_exit),
+                            y_begin, rows if y_end is None else y_end,
+                            None if D is None else _ptr(D, ctypes.c_double),
+                            None if margins is None else _ptr(margins, ctypes.c_double), ctypes.byref(st))
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    return StepResult(grid, D, margins, n_valid, st.visited, st.nominal, np.zeros((0, 2), np.int32))
+
+
+def select_from_D(D: np.ndarray, grid: np.ndarray, repeat_range: int, repeat_addition: int) -> np.ndarray:
+    D = np.ascontiguousarray(D, np.float64)
+    grid = np.ascontiguousarray(grid, np.int64).copy()
+    lib().mo_select_from_D(_ptr(D, ctypes.c_double), D.shape[1], _ptr(grid, ctypes.c_int64), grid.shape[0], grid.shape[1],
+                           repeat_range, repeat_addition)
+    return grid
+
+
+def generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid_states: list, diff_type: int = RGB_EUCLIDEAN,
+             scheme: int = SCHEME_NONE, repeat_range: int = 0, repeat_addition: int = 0, want_D: bool = True,
+             early_exit: bool = True, shared_buffer_quirk: bool = True) -> list:
+    """CPUPhotomosaicGenerator::generateBestFits (CPUPhotomosaicGenerator.cpp:33-112): list of StepResult."""
+    mains = [to_working_space(v, diff_type) for v in colour_scheme_variants(main_bgr8, scheme)]
+    lib_f32 = preprocess_library(lib_bgr8, group, diff_type)
+    results = []
+    for step, g in enumerate(grid_states):
+        cells, bounds, flips, coords = extract_cells(mains, group, step, g, shared_buffer_quirk)
+        masks4 = group.detail_cells[step].masks4()
+        assert lib_f32.shape[1] == masks4.shape[1], "library / detail-mask size mismatch (SURVEY Q4)"
+        r = generate_step(diff_type, cells, bounds, flips, lib_f32, masks4, g, repeat_range, repeat_addition,
+                          want_D=want_D, early_exit=early_exit)
+        r.coords = coords
+        results.append(r)
+        if step + 1 < len(grid_states):
+            lib_f32 = halve_library(lib_f32)
+    return results

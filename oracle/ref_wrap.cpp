@@ -1,0 +1,47 @@
+// C entry points over the reference's own ColourDifference.cpp and GridUtility.cpp, which
+// oracle/Makefile compiles unmodified from /root/reference into oracle/_ref/libref_core.so.
+// Test infrastructure only: used to validate the oracle's restatement (tests/test_oracle_ref.py).
+#include <optional>
+#include "ColourDifference.h"
+#include "GridUtility.h"
+
+static CellShape make_shape(const int *p)
+{
+    CellShape s;
+    s.size = p[0]; s.rowSpacing = p[1]; s.colSpacing = p[2]; s.altRowSpacing = p[3]; s.altColSpacing = p[4];
+    s.altRowOffset = p[5]; s.altColOffset = p[6];
+    s.colFlipH = p[7]; s.colFlipV = p[8]; s.rowFlipH = p[9]; s.rowFlipV = p[10];
+    return s;
+}
+
+extern "C" {
+double ref_rgb_euclidean(const double *a, const double *b)
+{
+    return ColourDifference::calculateRGBEuclidean(cv::Vec3d(a[0], a[1], a[2]), cv::Vec3d(b[0], b[1], b[2]));
+}
+double ref_ciede2000(const double *a, const double *b)
+{
+    return ColourDifference::calculateCIEDE2000(cv::Vec3d(a[0], a[1], a[2]), cv::Vec3d(b[0], b[1], b[2]));
+}
+// same call the generator makes: a std::function taking Vec3d fed with Vec3f pixels
+double ref_diff_f32(int type, const float *a, const float *b)
+{
+    const auto f = ColourDifference::getFunction(static_cast<ColourDifference::Type>(type));
+    return f(cv::Vec3f(a[0], a[1], a[2]), cv::Vec3f(b[0], b[1], b[2]));
+}
+void ref_grid_size(const int *shape, int w, int h, int pad, int *gx, int *gy)
+{
+    const cv::Point p = GridUtility::calculateGridSize(make_shape(shape), w, h, pad);
+    *gx = p.x; *gy = p.y;
+}
+void ref_rect_at(const int *shape, int x, int y, int *rect)
+{
+    const cv::Rect r = GridUtility::getRectAt(make_shape(shape), x, y);
+    rect[0] = r.x; rect[1] = r.y; rect[2] = r.width; rect[3] = r.height;
+}
+int ref_flip_at(const int *shape, int x, int y)
+{
+    const auto f = GridUtility::getFlipStateAt(make_shape(shape), x, y);
+    return (f.horizontal ? 1 : 0) + (f.vertical ? 2 : 0);
+}
+}
