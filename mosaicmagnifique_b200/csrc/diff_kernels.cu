@@ -1,0 +1,205 @@
+// Fused masked difference-sum kernel: D[cell, lib] = sum_p w[cell,p] * diff(cell[p], lib[p]).
+//
+// Replaces, in ONE launch per size step, the reference's per-(cell, library image) chain
+//   imageDifference / imageDifferenceEdge  src/Photomosaic/CUDA/PhotomosaicGenerator.cu:35-72
+//   reduceAdd tree + D2D copies            src/Photomosaic/CUDA/Reduction.cu:24-211
+//   flattenKernel                          src/Photomosaic/CUDA/PhotomosaicGenerator.cu:201-209
+// and, when no repeat penalty is active, findLowestKernel (:175-189) through the argmin epilogue.
+// CPU semantics followed: CPUPhotomosaicGenerator.cpp:137-169 (masked, bounded sum; strict <,
+// lowest index wins).
+//
+// Data layout (built by prep_kernels.cu):
+//   lib  : float4 (x0,x1,x2,C)  [lib_tile][chunk][TNB][KP]   one contiguous 16 KB block per (tile, chunk)
+//   cell : float4 (x0,x1,x2,C)  [cell_tile][chunk][TCB][KP]  followed by float w[TCB][KP] -> 20 KB block
+//   w = 1 where the (flipped) detail mask is set and the pixel lies inside the cell's detail-space bound,
+//   else 0; pixels are stored in the compacted order of the step's active-pixel list, padded with w = 0.
+//
+// Kernel shape: one CTA = 8 consumer warps + 1 producer warp. The producer lane streams (cell block,
+// lib block) pairs into a 3-stage shared-memory ring with cp.async.bulk (TMA bulk copy, UBLKCP in SASS)
+// completing on "full" mbarriers; consumers release stages through "empty" mbarriers. Consumer warp w
+// owns cell w of the tile, its 32 lanes stride the chunk's pixels (conflict-free LDS.128), and every lane
+// keeps TNB running sums, reduced with warp shuffles at the end. Roofline: FP32 + MUFU issue.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "colour_math.cuh"
+#include "kernels.h"
+
+namespace mm {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int DIFF>
+__device__ __forceinline__ float pixel_diff(const float4 &c, const float4 &l)
+{
+    if (DIFF == MM_DIFF_CIEDE2000)
+        return mm_ciede2000(c.x, c.y, c.z, c.w, l.x, l.y, l.z, l.w);
+    return mm_euclid(c.x, c.y, c.z, l.x, l.y, l.z);
+}
+
+constexpr int kStages = 3;
+constexpr int kConsumerWarps = MM_TCB;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr uint32_t kLibBlockBytes = MM_TNB * MM_KP * 16;
+constexpr uint32_t kCellBlockBytes = MM_TCB * MM_KP * 20;
+constexpr uint32_t kStageBytes = kLibBlockBytes + kCellBlockBytes;
+
+template <int DIFF>
+__global__ void __launch_bounds__(kThreads, 2)
+diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__restrict__ lib, float *__restrict__ D,
+                unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t full_bar[kStages];
+    __shared__ uint64_t empty_bar[kStages];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell_tile = blockIdx.x, lib_tile = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer warp: one elected lane drives the TMA ring
+        if (lane == 0) {
+            const unsigned char *cell_src = cells + (size_t)cell_tile * n_chunks * kCellBlockBytes;
+            const unsigned char *lib_src = lib + (size_t)lib_tile * n_chunks * kLibBlockBytes;
+            for (int k = 0; k < n_chunks; ++k) {
+                const int s = k % kStages;
+                if (k >= kStages)
+                    mbar_wait(&empty_bar[s], ((k / kStages) - 1) & 1);
+                unsigned char *dst = smem + (size_t)s * kStageBytes;
+                mbar_expect_tx(&full_bar[s], kStageBytes);
+                bulk_g2s(dst, lib_src + (size_t)k * kLibBlockBytes, kLibBlockBytes, &full_bar[s]);
+                bulk_g2s(dst + kLibBlockBytes, cell_src + (size_t)k * kCellBlockBytes, kCellBlockBytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps: warp = cell within the tile, lanes stride pixels
+    float acc[MM_TNB];
+#pragma unroll
+    for (int i = 0; i < MM_TNB; ++i)
+        acc[i] = 0.0f;
+
+    for (int k = 0; k < n_chunks; ++k) {
+        const int s = k % kStages;
+        mbar_wait(&full_bar[s], (k / kStages) & 1);
+        const float4 *lib_s = reinterpret_cast<const float4 *>(smem + (size_t)s * kStageBytes);
+        const float4 *cell_s = reinterpret_cast<const float4 *>(smem + (size_t)s * kStageBytes + kLibBlockBytes) + warp * MM_KP;
+        const float *w_s = reinterpret_cast<const float *>(smem + (size_t)s * kStageBytes + kLibBlockBytes + MM_TCB * MM_KP * 16) + warp * MM_KP;
+#pragma unroll 1
+        for (int j = 0; j < MM_KP / 32; ++j) {
+            const int p = j * 32 + lane;
+            const float4 c = cell_s[p];
+            const float w = w_s[p];
+#pragma unroll
+            for (int i = 0; i < MM_TNB; ++i) {
+                const float4 l = lib_s[i * MM_KP + p];
+                acc[i] = fmaf(w, pixel_diff<DIFF>(c, l), acc[i]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(&empty_bar[s]);
+    }
+
+    // ---------------- epilogue: warp-shuffle reduction, D store, fused argmin
+#pragma unroll
+    for (int i = 0; i < MM_TNB; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+        acc[i] = v;
+    }
+    const int cell = cell_tile * MM_TCB + warp;
+    if (lane < MM_TNB) {
+        float v = 0.0f;
+#pragma unroll
+        for (int i = 0; i < MM_TNB; ++i)
+            v = (lane == i) ? acc[i] : v;
+        const int li = lib_tile * MM_TNB + lane;
+        if (D)
+            D[(size_t)cell * n_lib_pad + li] = v;
+        if (best_key && li < n_lib && cell < n_cells) {
+            // non-negative floats order like their bit patterns; low word = index -> lowest index wins ties
+            const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)li;
+            atomicMin(best_key + cell, key);
+        }
+    }
+}
+
+template <int DIFF>
+static cudaError_t launch(const void *cells, const void *lib, float *D, unsigned long long *best_key, int n_cell_tiles,
+                          int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream)
+{
+    const size_t smem = (size_t)kStages * kStageBytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(diff_sum_kernel<DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+        configured = true;
+    }
+    dim3 grid(n_cell_tiles, n_lib_tiles);
+    diff_sum_kernel<DIFF><<<grid, kThreads, smem, stream>>>((const unsigned char *)cells, (const unsigned char *)lib, D,
+                                                             best_key, n_chunks, n_lib, n_lib_tiles * MM_TNB, n_cells);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, float *D, unsigned long long *best_key,
+                            int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream)
+{
+    if (n_cell_tiles <= 0 || n_lib_tiles <= 0 || n_chunks <= 0)
+        return cudaSuccess;
+    if (n_lib_tiles > 65535)
+        return cudaErrorInvalidValue;
+    if (diff_type == MM_DIFF_CIEDE2000)
+        return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream);
+    return launch<MM_DIFF_EUCLID>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream);
+}
+
+}  // namespace mm

@@ -1,0 +1,1001 @@
+// Host orchestration + C ABI (include/mosaic_b200.h) of the B200 photomosaic best-fit engine.
+//
+// Mirrors the reference's generator object
+//   PhotomosaicGeneratorBase   src/Photomosaic/PhotomosaicGeneratorBase.{h,cpp}
+//   CUDAPhotomosaicGenerator   src/Photomosaic/CUDA/CUDAPhotomosaicGenerator.{h,cpp}
+// but with a different execution plan: instead of ~3 * N_lib launches and 17 stream syncs PER CELL
+// (CUDAPhotomosaicGenerator.cpp:231-292) a size step is a fixed handful of launches on one stream:
+//   to_working_space (main) -> [area_u8] -> to_working_space (library) -> pack_library -> extract_cells
+//   -> diff_sum (cells x library, one launch) -> [min_variants] -> [topk] -> select / keys_to_grid.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/mosaic_b200.h"
+#include "host_model.h"
+#include "kernels.h"
+
+extern "C" const int16_t mm_lab_lut_s16[];  // lab_lut.S
+
+namespace {
+
+using namespace mm;
+
+struct Fail {
+    int code;
+    std::string msg;
+};
+
+#define CU(expr)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (expr);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            throw Fail{e__ == cudaErrorMemoryAllocation ? MOSAIC_ERR_OUT_OF_MEMORY : MOSAIC_ERR_CUDA,          \
+                       std::string(#expr) + ": " + cudaGetErrorString(e__)};                                  \
+    } while (0)
+
+// stream-ordered device buffer (cudaMallocAsync pool: reused across generate() calls)
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t stream = nullptr;
+    void alloc(size_t n, cudaStream_t s)
+    {
+        release();
+        stream = s;
+        if (n == 0)
+            return;
+        CU(cudaMallocAsync(&p, n, s));
+        bytes = n;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeAsync(p, stream);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), stream(o.stream)
+    {
+        o.p = nullptr;
+        o.bytes = 0;
+    }
+    DevBuf &operator=(DevBuf &&o) noexcept
+    {
+        if (this != &o) {
+            release();
+            p = o.p;
+            bytes = o.bytes;
+            stream = o.stream;
+            o.p = nullptr;
+            o.bytes = 0;
+        }
+        return *this;
+    }
+};
+
+struct StepPlan {
+    int rows = 0, cols = 0;
+    int S = 0, ds = 0, k = 1;          // normal size, detail size, integer reduction factor
+    int n_active = 0, n_chunks = 0;    // compacted pixels of the detail mask (union of the 4 flips)
+    std::vector<int> cell_pos;         // valid cells, raster order: y * cols + x (padded coordinates)
+    std::vector<int> next_x;           // next valid column in the same row
+    std::vector<int> row_first;        // per grid row: column of the first valid cell (cols if none)
+    int64_t cell_begin = 0, cell_end = 0;  // this rank's block of valid cells
+    double pixel_diffs = 0, pixel_diffs_nominal = 0;
+};
+
+}  // namespace
+
+struct mosaic_generator {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int sm_count = 0;
+
+    // inputs
+    int img_rows = 0, img_cols = 0;
+    DevBuf d_main_u8;
+    std::vector<uint8_t> h_main;  // kept for compute_grid_state (host entropy rule)
+    int64_t n_lib = 0;
+    int lib_size = 0;
+    DevBuf d_lib_u8;
+    int diff_type = MOSAIC_RGB_EUCLIDEAN;
+    int scheme = MOSAIC_SCHEME_NONE;
+    bool quirk_faithful = true;
+    Group group;
+    bool have_group = false;
+    std::vector<GridStep> grid;  // state in, best fits out
+    int repeat_range = 0, repeat_addition = 0;
+    bool keep_D = false;
+    int rank = 0, world = 1;
+
+    mosaic_progress_fn progress_fn = nullptr;
+    void *progress_user = nullptr;
+    std::atomic<bool> cancelled{false};
+
+    // products
+    DevBuf d_lut;
+    std::vector<StepPlan> plans;
+    std::vector<DevBuf> d_D;            // per step [n_local_cells_pad * V][n_lib_pad]
+    std::vector<DevBuf> d_cand_score, d_cand_idx;
+    std::vector<int> cand_k;
+    int V_eff = 1;
+    mosaic_timings timings{};
+
+    int fail(int code, const std::string &msg)
+    {
+        error = msg;
+        return code;
+    }
+};
+
+namespace {
+
+using G = mosaic_generator;
+
+int guard(G *g, const char *what, void (*fn)(G *, void *), void *arg)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    try {
+        cudaError_t e = cudaSetDevice(g->device);
+        if (e != cudaSuccess)
+            throw Fail{MOSAIC_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+        fn(g, arg);
+        g->error.clear();
+        return MOSAIC_OK;
+    } catch (const Fail &f) {
+        cudaGetLastError();
+        return g->fail(f.code, std::string(what) + ": " + f.msg);
+    } catch (const std::bad_alloc &) {
+        return g->fail(MOSAIC_ERR_OUT_OF_MEMORY, std::string(what) + ": host allocation failed");
+    } catch (const std::exception &e) {
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, std::string(what) + ": " + e.what());
+    }
+}
+
+void shape_from_c(const mosaic_cell_shape &c, const uint8_t *mask, Shape &s)
+{
+    s.set_mask(mask, c.size);
+    s.row_spacing = c.row_spacing;
+    s.col_spacing = c.col_spacing;
+    s.alt_row_spacing = c.alt_row_spacing;
+    s.alt_col_spacing = c.alt_col_spacing;
+    s.alt_row_offset = c.alt_row_offset;
+    s.alt_col_offset = c.alt_col_offset;
+    s.alt_col_flip_h = c.alt_col_flip_h != 0;
+    s.alt_col_flip_v = c.alt_col_flip_v != 0;
+    s.alt_row_flip_h = c.alt_row_flip_h != 0;
+    s.alt_row_flip_v = c.alt_row_flip_v != 0;
+}
+
+void shape_to_c(const Shape &s, mosaic_cell_shape &c)
+{
+    c.size = s.size;
+    c.row_spacing = s.row_spacing;
+    c.col_spacing = s.col_spacing;
+    c.alt_row_spacing = s.alt_row_spacing;
+    c.alt_col_spacing = s.alt_col_spacing;
+    c.alt_row_offset = s.alt_row_offset;
+    c.alt_col_offset = s.alt_col_offset;
+    c.alt_col_flip_h = s.alt_col_flip_h;
+    c.alt_col_flip_v = s.alt_col_flip_v;
+    c.alt_row_flip_h = s.alt_row_flip_h;
+    c.alt_row_flip_v = s.alt_row_flip_v;
+}
+
+Shape shape_params_only(const mosaic_cell_shape &c)
+{
+    Shape s;
+    s.size = c.size;
+    s.row_spacing = c.row_spacing;
+    s.col_spacing = c.col_spacing;
+    s.alt_row_spacing = c.alt_row_spacing;
+    s.alt_col_spacing = c.alt_col_spacing;
+    s.alt_row_offset = c.alt_row_offset;
+    s.alt_col_offset = c.alt_col_offset;
+    s.alt_col_flip_h = c.alt_col_flip_h != 0;
+    s.alt_col_flip_v = c.alt_col_flip_v != 0;
+    s.alt_row_flip_h = c.alt_row_flip_h != 0;
+    s.alt_row_flip_v = c.alt_row_flip_v != 0;
+    return s;
+}
+
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit Timer(cudaStream_t st) : s(st)
+    {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+    }
+    ~Timer()
+    {
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+    void start() { cudaEventRecord(a, s); }
+    void stop() { cudaEventRecord(b, s); }
+    double ms()
+    {
+        float m = 0;
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&m, a, b);
+        return m;
+    }
+};
+
+// ------------------------------------------------------------------ planning
+
+void check_ready(G *g)
+{
+    if (g->img_rows == 0)
+        throw Fail{MOSAIC_ERR_NOT_READY, "no main image set"};
+    if (g->n_lib == 0)
+        throw Fail{MOSAIC_ERR_NOT_READY, "no library set (the reference would find no best fit)"};
+    if (!g->have_group)
+        throw Fail{MOSAIC_ERR_NOT_READY, "no cell group set"};
+    if (g->grid.empty())
+        throw Fail{MOSAIC_ERR_NOT_READY, "no grid state set"};
+    if ((int)g->grid.size() > g->group.size_steps + 1)
+        throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "grid state has more steps than the cell group"};
+    if (g->lib_size != g->group.cells[0].size)
+        throw Fail{MOSAIC_ERR_INVALID_ARGUMENT,
+                   "library images must be at the cell size (the reference resizes them before setLibrary, MainWindow.cpp:575-581)"};
+    if (g->scheme != MOSAIC_SCHEME_NONE)
+        throw Fail{MOSAIC_ERR_UNSUPPORTED, "colour schemes other than NONE are not implemented yet"};
+}
+
+void make_plans(G *g)
+{
+    const Group &grp = g->group;
+    g->plans.assign(g->grid.size(), StepPlan());
+    int lib_ds = 0;
+    for (size_t s = 0; s < g->grid.size(); ++s) {
+        StepPlan &p = g->plans[s];
+        const GridStep &gs = g->grid[s];
+        p.rows = gs.rows;
+        p.cols = gs.cols;
+        p.S = grp.cells[s].size;
+        p.ds = grp.detail_cells[s].size;
+        // library size at this step: round(detail size) at step 0, round(0.5 * previous) afterwards
+        // (PhotomosaicGeneratorBase.cpp:262, ImageUtility.cpp:97-98); must agree with the detail mask
+        if (s == 0)
+            lib_ds = (grp.detail != 1.0) ? p.ds : g->lib_size;
+        else {
+            if (lib_ds % 2 != 0)
+                throw Fail{MOSAIC_ERR_UNSUPPORTED, "odd library size at a size step (the reference indexes out of range here)"};
+            lib_ds /= 2;
+        }
+        if (lib_ds != p.ds)
+            throw Fail{MOSAIC_ERR_UNSUPPORTED,
+                       "library size and detail mask size disagree at step " + std::to_string(s) +
+                           " (the reference reads out of range for this cell size / detail combination)"};
+        if (p.S % p.ds != 0)
+            throw Fail{MOSAIC_ERR_UNSUPPORTED, "detail level must divide the cell size (fractional INTER_AREA for cells is not implemented yet)"};
+        p.k = p.S / p.ds;
+        if (s == 0 && grp.detail != 1.0 && g->lib_size % p.ds != 0)
+            throw Fail{MOSAIC_ERR_UNSUPPORTED, "library detail resize needs an integer ratio"};
+
+        int gx, gy;
+        grid_size(grp.cells[s], g->img_cols, g->img_rows, kPadGrid, gx, gy);
+        if (gx != gs.cols || gy != gs.rows)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "grid state of step " + std::to_string(s) + " is " + std::to_string(gs.rows) + "x" +
+                                                        std::to_string(gs.cols) + " but the cell group needs " + std::to_string(gy) + "x" +
+                                                        std::to_string(gx)};
+        p.row_first.assign(gs.rows, gs.cols);
+        for (int y = 0; y < gs.rows; ++y) {
+            int prev = -1;
+            for (int x = 0; x < gs.cols; ++x)
+                if (gs.v[(size_t)y * gs.cols + x] >= 0) {
+                    if (prev < 0)
+                        p.row_first[y] = x;
+                    else
+                        p.next_x[prev] = x;
+                    prev = (int)p.cell_pos.size();
+                    p.cell_pos.push_back(y * gs.cols + x);
+                    p.next_x.push_back(gs.cols);
+                }
+        }
+        // rank's block of cells: contiguous grid rows, balanced by valid-cell count
+        const int64_t n = (int64_t)p.cell_pos.size();
+        auto row_start_cell = [&](int64_t target) {
+            // first cell index >= target that starts a grid row
+            int64_t c = std::min(target, n);
+            while (c > 0 && c < n && p.cell_pos[c] / gs.cols == p.cell_pos[c - 1] / gs.cols)
+                ++c;
+            return c;
+        };
+        p.cell_begin = g->rank == 0 ? 0 : row_start_cell(n * g->rank / g->world);
+        p.cell_end = g->rank == g->world - 1 ? n : row_start_cell(n * (g->rank + 1) / g->world);
+        if (p.cell_end < p.cell_begin)
+            p.cell_end = p.cell_begin;
+    }
+}
+
+// ------------------------------------------------------------------ the pipeline
+
+struct StepDev {
+    DevBuf pix_list, masks4, descs, cells_packed, lib_packed, best_key;
+};
+
+void run_pipeline(G *g, bool candidates_only)
+{
+    check_ready(g);
+    make_plans(g);
+    cudaStream_t st = g->stream;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    g->timings = mosaic_timings{};
+    mosaic_timings &tm = g->timings;
+    const bool is_lab = g->diff_type != MOSAIC_RGB_EUCLIDEAN;
+    const bool with_chroma = g->diff_type == MOSAIC_CIEDE2000;
+    const int kern_type = with_chroma ? MM_DIFF_CIEDE2000 : MM_DIFF_EUCLID;
+    const int V = 1;  // scheme NONE only for now (faithful quirk mode also compares a single variant)
+    g->V_eff = V;
+    const int64_t N = g->n_lib;
+    const int n_lib_tiles = (int)((N + MM_TNB - 1) / MM_TNB);
+    const int n_lib_pad = n_lib_tiles * MM_TNB;
+    const size_t n_steps = g->grid.size();
+    Timer t_pre(st), t_diff(st), t_sel(st);
+    double pre_ms = 0, diff_ms = 0, sel_ms = 0;
+
+    if (!g->d_lut.p) {
+        g->d_lut.alloc(33 * 33 * 33 * 3 * sizeof(int16_t), st);
+        CU(cudaMemcpyAsync(g->d_lut.p, mm_lab_lut_s16, g->d_lut.bytes, cudaMemcpyHostToDevice, st));
+        tm.h2d_bytes += (double)g->d_lut.bytes;
+    }
+
+    // ---- Preprocess: main image -> working space (PhotomosaicGeneratorBase.cpp:223-252)
+    t_pre.start();
+    DevBuf d_main_f32;
+    d_main_f32.alloc((size_t)g->img_rows * g->img_cols * 3 * sizeof(float), st);
+    CU(launch_to_working_space(g->d_main_u8.as<uint8_t>(), (size_t)g->img_cols * 3, g->img_rows, g->img_cols,
+                               d_main_f32.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
+    tm.kernel_launches++;
+
+    // ---- Preprocess: library -> working space at the detail size of step 0 (:255-290)
+    DevBuf d_lib_work, d_lib_small;
+    int lib_ds = g->lib_size;
+    {
+        const uint8_t *src = g->d_lib_u8.as<uint8_t>();
+        if (g->group.detail != 1.0) {
+            const int k = g->lib_size / g->plans[0].ds;
+            lib_ds = g->plans[0].ds;
+            d_lib_small.alloc((size_t)N * lib_ds * lib_ds * 3, st);
+            CU(launch_area_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, k, st));
+            tm.kernel_launches++;
+            src = d_lib_small.as<uint8_t>();
+        }
+        d_lib_work.alloc((size_t)N * lib_ds * lib_ds * 3 * sizeof(float), st);
+        // the library is one tall image of N * ds rows
+        CU(launch_to_working_space(src, (size_t)lib_ds * 3, (int)std::min<int64_t>(N * lib_ds, INT32_MAX), lib_ds,
+                                   d_lib_work.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
+        tm.kernel_launches++;
+        d_lib_small.release();
+    }
+    t_pre.stop();
+    pre_ms += t_pre.ms();
+
+    g->d_D.clear();
+    g->d_D.resize(n_steps);
+    g->d_cand_score.clear();
+    g->d_cand_score.resize(n_steps);
+    g->d_cand_idx.clear();
+    g->d_cand_idx.resize(n_steps);
+    g->cand_k.assign(n_steps, 0);
+
+    const bool penalise = g->repeat_range > 0 && g->repeat_addition != 0;
+    int progress = 0;
+
+    for (size_t s = 0; s < n_steps; ++s) {
+        if (g->cancelled.load())
+            throw Fail{MOSAIC_ERR_CANCELLED, "cancelled"};
+        StepPlan &p = g->plans[s];
+        const Shape &normal = g->group.cells[s];
+        const Shape &dshape = g->group.detail_cells[s];
+        GridStep &gs = g->grid[s];
+        const int ds = p.ds, P = ds * ds;
+        StepDev d;
+
+        t_pre.start();
+        if (s > 0) {
+            // halve the working-space library (CPUPhotomosaicGenerator.cpp:95-99)
+            DevBuf half;
+            half.alloc((size_t)N * P * 3 * sizeof(float), st);
+            CU(launch_area_f32(d_lib_work.as<float>(), half.as<float>(), N, ds * 2, 2, st));
+            tm.kernel_launches++;
+            std::swap(d_lib_work.p, half.p);
+            std::swap(d_lib_work.bytes, half.bytes);
+        }
+
+        // active pixel list: union of the four flipped detail masks, raster order
+        const std::vector<uint8_t> m4 = dshape.masks4();
+        std::vector<int> pix;
+        pix.reserve(P);
+        for (int i = 0; i < P; ++i)
+            if (m4[i] | m4[(size_t)P + i] | m4[(size_t)2 * P + i] | m4[(size_t)3 * P + i])
+                pix.push_back(i);
+        p.n_active = (int)pix.size();
+        p.n_chunks = std::max(1, (p.n_active + MM_KP - 1) / MM_KP);
+        d.pix_list.alloc(std::max<size_t>(pix.size(), 1) * sizeof(int), st);
+        CU(cudaMemcpyAsync(d.pix_list.p, pix.data(), pix.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        d.masks4.alloc(m4.size(), st);
+        CU(cudaMemcpyAsync(d.masks4.p, m4.data(), m4.size(), cudaMemcpyHostToDevice, st));
+        tm.h2d_bytes += (double)(pix.size() * sizeof(int) + m4.size());
+
+        // library tiles
+        d.lib_packed.alloc((size_t)n_lib_tiles * p.n_chunks * (MM_TNB * MM_KP * 16), st);
+        CU(launch_pack_library(d_lib_work.as<float>(), d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
+                               n_lib_tiles, with_chroma, st));
+        tm.kernel_launches++;
+
+        // cell descriptors of this rank's cells (getCellAt, PhotomosaicGeneratorBase.cpp:293-329)
+        const int64_t n_local = p.cell_end - p.cell_begin;
+        const int64_t n_all = (int64_t)p.cell_pos.size();
+        std::vector<CellDesc> descs((size_t)n_local * V);
+        // mask pixel counts through integral images (for the pixel-diff statistics)
+        std::vector<std::vector<int>> integ(4, std::vector<int>((size_t)(ds + 1) * (ds + 1), 0));
+        for (int f = 0; f < 4; ++f)
+            for (int y = 0; y < ds; ++y)
+                for (int x = 0; x < ds; ++x)
+                    integ[f][(size_t)(y + 1) * (ds + 1) + x + 1] = (m4[((size_t)f * ds + y) * ds + x] != 0) + integ[f][(size_t)y * (ds + 1) + x + 1] +
+                                                                  integ[f][(size_t)(y + 1) * (ds + 1) + x] - integ[f][(size_t)y * (ds + 1) + x];
+        for (int64_t c = 0; c < n_all; ++c) {
+            const int pos = p.cell_pos[c];
+            const int x = pos % p.cols - kPadGrid, y = pos / p.cols - kPadGrid;
+            const Rect r = rect_at(normal, x, y);
+            const Rect b = detail_bound(normal, ds, g->group.detail, x, y, g->img_cols, g->img_rows);
+            const int flip = flip_at(normal, x, y);
+            const std::vector<int> &I = integ[flip];
+            const int act = I[(size_t)(b.y + b.h) * (ds + 1) + b.x + b.w] - I[(size_t)b.y * (ds + 1) + b.x + b.w] -
+                            I[(size_t)(b.y + b.h) * (ds + 1) + b.x] + I[(size_t)b.y * (ds + 1) + b.x];
+            p.pixel_diffs += (double)act * N * V;
+            p.pixel_diffs_nominal += (double)P * N * V;
+            if (c >= p.cell_begin && c < p.cell_end)
+                for (int v = 0; v < V; ++v)
+                    descs[(size_t)(c - p.cell_begin) * V + v] = CellDesc{r.x, r.y, b.x, b.y, b.w, b.h, flip, v};
+        }
+        tm.pixel_diffs += p.pixel_diffs;
+        tm.pixel_diffs_nominal += p.pixel_diffs_nominal;
+
+        const int n_rows_local = (int)(n_local * V);
+        const int n_cell_tiles = (n_rows_local + MM_TCB - 1) / MM_TCB;
+        const int n_rows_pad = n_cell_tiles * MM_TCB;
+        d.descs.alloc(std::max<size_t>(descs.size(), 1) * sizeof(CellDesc), st);
+        CU(cudaMemcpyAsync(d.descs.p, descs.data(), descs.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, st));
+        tm.h2d_bytes += (double)(descs.size() * sizeof(CellDesc));
+        d.cells_packed.alloc((size_t)std::max(n_cell_tiles, 1) * p.n_chunks * (MM_TCB * MM_KP * 20), st);
+        CU(launch_extract_cells(d_main_f32.as<float>(), g->img_rows, g->img_cols, d.descs.as<CellDesc>(), n_rows_local, p.S, p.k,
+                                d.masks4.as<uint8_t>(), d.pix_list.as<int>(), p.n_active, p.n_chunks, d.cells_packed.p,
+                                with_chroma, st));
+        tm.kernel_launches++;
+        t_pre.stop();
+        pre_ms += t_pre.ms();
+
+        // ---- DiffReduce: one fused launch for the whole step
+        t_diff.start();
+        const bool fused_argmin = !penalise && V == 1 && !candidates_only && g->world == 1;
+        const bool need_D = !fused_argmin || g->keep_D;
+        DevBuf &D = g->d_D[s];
+        if (need_D)
+            D.alloc((size_t)std::max(n_rows_pad, 1) * n_lib_pad * sizeof(float), st);
+        if (fused_argmin) {
+            d.best_key.alloc((size_t)std::max(n_rows_pad, 1) * sizeof(unsigned long long), st);
+            CU(launch_fill_u64(d.best_key.as<unsigned long long>(), (size_t)std::max(n_rows_pad, 1), ~0ull, st));
+            tm.kernel_launches++;
+        }
+        CU(launch_diff_sum(kern_type, d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
+                           fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
+                           (int)N, n_rows_local, st));
+        if (n_cell_tiles > 0)
+            tm.kernel_launches++;
+        t_diff.stop();
+        diff_ms += t_diff.ms();
+
+        // ---- Repeats + FindLowest
+        t_sel.start();
+        if (V > 1 && need_D) {
+            CU(launch_min_variants(D.as<float>(), (int)n_local, V, n_lib_pad, st));
+            tm.kernel_launches++;
+        }
+        if (candidates_only) {
+            // K = min(N, 2r^2 + 2r + 1) smallest entries always contain the penalised winner
+            const int64_t r = g->repeat_range;
+            const int64_t kk = penalise ? std::min<int64_t>(N, 2 * r * r + 2 * r + 1) : 1;
+            const int K = (int)kk;
+            g->cand_k[s] = K;
+            g->d_cand_score[s].alloc((size_t)std::max<int64_t>(n_local, 1) * K * sizeof(float), st);
+            g->d_cand_idx[s].alloc((size_t)std::max<int64_t>(n_local, 1) * K * sizeof(int), st);
+            CU(launch_topk(D.as<float>(), V * n_lib_pad, (int)N, (int)n_local, K, g->d_cand_score[s].as<float>(),
+                           g->d_cand_idx[s].as<int>(), st));
+            if (n_local > 0)
+                tm.kernel_launches++;
+        } else {
+            DevBuf d_grid, d_pos, d_next, d_prog, d_counts;
+            d_grid.alloc(gs.v.size() * sizeof(long long), st);
+            CU(cudaMemcpyAsync(d_grid.p, gs.v.data(), gs.v.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+            d_pos.alloc(std::max<size_t>(p.cell_pos.size(), 1) * sizeof(int), st);
+            CU(cudaMemcpyAsync(d_pos.p, p.cell_pos.data(), p.cell_pos.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+            tm.h2d_bytes += (double)(gs.v.size() * sizeof(long long) + p.cell_pos.size() * sizeof(int));
+            if (fused_argmin) {
+                CU(launch_keys_to_grid(d.best_key.as<unsigned long long>(), d_pos.as<int>(), d_grid.as<long long>(), (int)n_all,
+                                       nullptr, st));
+                if (n_all > 0)
+                    tm.kernel_launches++;
+            } else {
+                d_next.alloc(std::max<size_t>(p.next_x.size(), 1) * sizeof(int), st);
+                CU(cudaMemcpyAsync(d_next.p, p.next_x.data(), p.next_x.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+                d_prog.alloc((size_t)p.rows * sizeof(int), st);
+                CU(cudaMemcpyAsync(d_prog.p, p.row_first.data(), (size_t)p.rows * sizeof(int), cudaMemcpyHostToDevice, st));
+                const int n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_all, select_max_ctas(g->device)));
+                d_counts.alloc((size_t)n_ctas * N * sizeof(int), st);
+                CU(cudaMemsetAsync(d_counts.p, 0, d_counts.bytes, st));
+                CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols,
+                                 D.as<float>(), nullptr, (int)N, V * n_lib_pad, (int)N, g->repeat_range, g->repeat_addition,
+                                 d_prog.as<int>(), d_counts.as<int>(), n_ctas, nullptr, st));
+                if (n_all > 0)
+                    tm.kernel_launches++;
+            }
+            CU(cudaMemcpyAsync(gs.v.data(), d_grid.p, gs.v.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+            tm.d2h_bytes += (double)(gs.v.size() * sizeof(long long));
+        }
+        t_sel.stop();
+        sel_ms += t_sel.ms();
+        if (!g->keep_D && !candidates_only)
+            D.release();
+        CU(cudaStreamSynchronize(st));
+
+        // progress(int): the reference emits per cell with weight 4^(steps-1-step) (CPUPhotomosaicGenerator.cpp:55, 87-88)
+        progress += (int)(pow(4.0, (double)(n_steps - 1 - s)) * p.rows * p.cols);
+        if (g->progress_fn)
+            g->progress_fn(progress, g->progress_user);
+    }
+    CU(cudaStreamSynchronize(st));
+    tm.preprocess_ms = pre_ms;
+    tm.diff_ms = diff_ms;
+    tm.select_ms = sel_ms;
+    tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+
+extern "C" {
+
+const char *mosaic_version(void) { return "mosaicmagnifique_b200 0.1 (sm_100a)"; }
+
+int mosaic_create(int device, mosaic_generator **out)
+{
+    if (!out)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return MOSAIC_ERR_CUDA;  // no CPU fallback by design
+    }
+    mosaic_generator *g = new (std::nothrow) mosaic_generator();
+    if (!g)
+        return MOSAIC_ERR_OUT_OF_MEMORY;
+    g->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete g;
+        return MOSAIC_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;  // keep freed blocks cached between generate() calls
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = g;
+    return MOSAIC_OK;
+}
+
+void mosaic_destroy(mosaic_generator *g)
+{
+    if (!g)
+        return;
+    cudaSetDevice(g->device);
+    if (g->stream)
+        cudaStreamSynchronize(g->stream);
+    g->d_main_u8.release();
+    g->d_lib_u8.release();
+    g->d_lut.release();
+    g->d_D.clear();
+    g->d_cand_score.clear();
+    g->d_cand_idx.clear();
+    if (g->stream) {
+        cudaStreamSynchronize(g->stream);
+        cudaStreamDestroy(g->stream);
+    }
+    delete g;
+}
+
+const char *mosaic_last_error(const mosaic_generator *g) { return g ? g->error.c_str() : "null generator"; }
+
+int mosaic_set_main_image(mosaic_generator *g, const uint8_t *bgr, int rows, int cols, size_t row_stride)
+{
+    struct A {
+        const uint8_t *bgr;
+        int rows, cols;
+        size_t stride;
+    } a{bgr, rows, cols, row_stride};
+    return guard(g, "setMainImage", [](G *g, void *p) {
+        A &a = *(A *)p;
+        if (!a.bgr || a.rows <= 0 || a.cols <= 0 || a.stride < (size_t)a.cols * 3)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "main image must be a non-empty 8U BGR image"};
+        g->d_main_u8.alloc((size_t)a.rows * a.cols * 3, g->stream);
+        CU(cudaMemcpy2DAsync(g->d_main_u8.p, (size_t)a.cols * 3, a.bgr, a.stride, (size_t)a.cols * 3, a.rows, cudaMemcpyHostToDevice,
+                             g->stream));
+        g->h_main.resize((size_t)a.rows * a.cols * 3);
+        for (int y = 0; y < a.rows; ++y)
+            memcpy(&g->h_main[(size_t)y * a.cols * 3], a.bgr + (size_t)y * a.stride, (size_t)a.cols * 3);
+        CU(cudaStreamSynchronize(g->stream));
+        g->img_rows = a.rows;
+        g->img_cols = a.cols;
+    }, &a);
+}
+
+int mosaic_set_library(mosaic_generator *g, const uint8_t *bgr, int64_t n, int size)
+{
+    struct A {
+        const uint8_t *bgr;
+        int64_t n;
+        int size;
+    } a{bgr, n, size};
+    return guard(g, "setLibrary", [](G *g, void *p) {
+        A &a = *(A *)p;
+        if (!a.bgr || a.n <= 0 || a.size <= 0)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "library must hold n > 0 square 8U BGR images"};
+        if (a.n * a.size > INT32_MAX)
+            throw Fail{MOSAIC_ERR_UNSUPPORTED, "library too large (n * size must fit 31 bits)"};
+        g->d_lib_u8.alloc((size_t)a.n * a.size * a.size * 3, g->stream);
+        CU(cudaMemcpyAsync(g->d_lib_u8.p, a.bgr, g->d_lib_u8.bytes, cudaMemcpyHostToDevice, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        g->n_lib = a.n;
+        g->lib_size = a.size;
+    }, &a);
+}
+
+int mosaic_set_colour_difference(mosaic_generator *g, int type)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (type < 0 || type > 2)
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setColourDifference: no function for given type");  // ColourDifference.cpp:23
+    g->diff_type = type;
+    return MOSAIC_OK;
+}
+
+int mosaic_set_colour_scheme(mosaic_generator *g, int type)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (type < 0 || type > 5)
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setColourScheme: no function for given type");  // ColourScheme.cpp:30
+    g->scheme = type;
+    return MOSAIC_OK;
+}
+
+int mosaic_set_variant_quirk(mosaic_generator *g, int faithful)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    g->quirk_faithful = faithful != 0;
+    return MOSAIC_OK;
+}
+
+int mosaic_set_cell_group(mosaic_generator *g, const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size, int detail_percent,
+                          int size_steps)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (!shape || !mask || shape->size <= 0)
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setCellGroup: missing shape or mask");
+    try {
+        Shape top;
+        shape_from_c(*shape, mask, top);
+        std::string err;
+        if (cell_size > 0 && cell_size != top.size) {
+            Shape r;
+            if (!top.resized(cell_size, r, err))
+                return g->fail(MOSAIC_ERR_UNSUPPORTED, "setCellGroup: " + err);
+            top = r;
+        }
+        Group grp;
+        if (!grp.build(top, detail_percent, size_steps, err))
+            return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setCellGroup: " + err);
+        g->group = grp;
+        g->have_group = true;
+        g->grid.clear();
+        return MOSAIC_OK;
+    } catch (const std::bad_alloc &) {
+        return g->fail(MOSAIC_ERR_OUT_OF_MEMORY, "setCellGroup: host allocation failed");
+    }
+}
+
+int mosaic_get_cell_shape(const mosaic_generator *g, int step, int detail, mosaic_cell_shape *out, uint8_t *mask_out, size_t mask_capacity)
+{
+    if (!g || !out || !g->have_group || step < 0 || step > g->group.size_steps)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    const Shape &s = detail ? g->group.detail_cells[step] : g->group.cells[step];
+    shape_to_c(s, *out);
+    if (mask_out) {
+        if (mask_capacity < s.mask.size())
+            return MOSAIC_ERR_INVALID_ARGUMENT;
+        memcpy(mask_out, s.mask.data(), s.mask.size());
+    }
+    return MOSAIC_OK;
+}
+
+int mosaic_set_grid_state(mosaic_generator *g, int step, int rows, int cols, const uint8_t *valid)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (!valid || step < 0 || rows <= 0 || cols <= 0 || step > (int)g->grid.size())
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setGridState: steps must be set in order with a rows x cols validity map");
+    if (step == (int)g->grid.size())
+        g->grid.emplace_back();
+    GridStep &gs = g->grid[step];
+    gs.rows = rows;
+    gs.cols = cols;
+    gs.v.resize((size_t)rows * cols);
+    for (size_t i = 0; i < gs.v.size(); ++i)
+        gs.v[i] = valid[i] ? 0 : -1;  // valid cells start as 0 (GridGenerator.cpp:192)
+    g->grid.resize(step + 1);
+    return MOSAIC_OK;
+}
+
+int mosaic_compute_grid_state(mosaic_generator *g)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (!g->have_group || g->img_rows == 0)
+        return g->fail(MOSAIC_ERR_NOT_READY, "getGridState: main image and cell group must be set");
+    std::string err;
+    if (!compute_grid_state(g->group, g->h_main.data(), g->img_rows, g->img_cols, (size_t)g->img_cols * 3, g->grid, err))
+        return g->fail(MOSAIC_ERR_UNSUPPORTED, "getGridState: " + err);
+    return MOSAIC_OK;
+}
+
+int mosaic_get_grid_steps(const mosaic_generator *g) { return g ? (int)g->grid.size() : MOSAIC_ERR_INVALID_ARGUMENT; }
+
+int mosaic_get_grid_size(const mosaic_generator *g, int step, int *rows, int *cols)
+{
+    if (!g || step < 0 || step >= (int)g->grid.size() || !rows || !cols)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    *rows = g->grid[step].rows;
+    *cols = g->grid[step].cols;
+    return MOSAIC_OK;
+}
+
+int mosaic_set_repeat(mosaic_generator *g, int range, int addition)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (range < 0 || addition < 0)
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setRepeat: range and addition must be >= 0");
+    g->repeat_range = range;
+    g->repeat_addition = addition;
+    return MOSAIC_OK;
+}
+
+int mosaic_generate(mosaic_generator *g)
+{
+    if (g && g->world != 1)
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "generateBestFits: sharded handles use mosaic_generate_candidates + mosaic_select_from_candidates");
+    return guard(g, "generateBestFits", [](G *g, void *) {
+        g->cancelled.store(false);
+        run_pipeline(g, false);
+    }, nullptr);
+}
+
+int mosaic_get_best_fits(const mosaic_generator *g, int step, int64_t *out, int rows, int cols)
+{
+    if (!g || !out || step < 0 || step >= (int)g->grid.size())
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    const GridStep &gs = g->grid[step];
+    if (rows != gs.rows || cols != gs.cols)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    memcpy(out, gs.v.data(), gs.v.size() * sizeof(int64_t));
+    return MOSAIC_OK;
+}
+
+int mosaic_get_max_progress(const mosaic_generator *g)
+{
+    if (!g || g->grid.empty())
+        return 0;
+    // PhotomosaicGeneratorBase.cpp:210-214
+    return (int)(pow(4.0, (double)g->grid.size() - 1) * (double)g->grid.size() * g->grid[0].cols * g->grid[0].rows);
+}
+
+void mosaic_set_progress_callback(mosaic_generator *g, mosaic_progress_fn fn, void *user)
+{
+    if (!g)
+        return;
+    g->progress_fn = fn;
+    g->progress_user = user;
+}
+
+void mosaic_cancel(mosaic_generator *g)
+{
+    if (g)
+        g->cancelled.store(true);
+}
+
+int mosaic_set_keep_differences(mosaic_generator *g, int keep)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    g->keep_D = keep != 0;
+    return MOSAIC_OK;
+}
+
+int64_t mosaic_get_valid_cell_count(const mosaic_generator *g, int step)
+{
+    if (!g || step < 0 || step >= (int)g->grid.size())
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (step < (int)g->plans.size())
+        return (int64_t)g->plans[step].cell_pos.size();
+    int64_t n = 0;
+    for (int64_t v : g->grid[step].v)
+        n += v >= 0;
+    return n;
+}
+
+int mosaic_get_differences(const mosaic_generator *g, int step, float *out, int64_t n_cells, int64_t n_lib)
+{
+    if (!g || !out || step < 0 || step >= (int)g->d_D.size() || !g->d_D[step].p)
+        return MOSAIC_ERR_NOT_READY;
+    const StepPlan &p = g->plans[step];
+    const int64_t n_local = p.cell_end - p.cell_begin;
+    if (n_cells != n_local || n_lib != g->n_lib)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (n_local == 0)
+        return MOSAIC_OK;
+    const int n_lib_pad = (int)((g->n_lib + MM_TNB - 1) / MM_TNB) * MM_TNB;
+    cudaSetDevice(g->device);
+    cudaError_t e = cudaMemcpy2D(out, (size_t)n_lib * sizeof(float), g->d_D[step].p, (size_t)g->V_eff * n_lib_pad * sizeof(float),
+                                 (size_t)n_lib * sizeof(float), (size_t)n_local, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? MOSAIC_OK : MOSAIC_ERR_CUDA;
+}
+
+int mosaic_get_timings(const mosaic_generator *g, mosaic_timings *out)
+{
+    if (!g || !out)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    *out = g->timings;
+    return MOSAIC_OK;
+}
+
+// ---- sharding
+
+int mosaic_set_shard(mosaic_generator *g, int rank, int world)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (world < 1 || rank < 0 || rank >= world)
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setShard: need 0 <= rank < world");
+    g->rank = rank;
+    g->world = world;
+    return MOSAIC_OK;
+}
+
+int mosaic_generate_candidates(mosaic_generator *g)
+{
+    return guard(g, "generateCandidates", [](G *g, void *) {
+        g->cancelled.store(false);
+        run_pipeline(g, true);
+    }, nullptr);
+}
+
+int mosaic_get_candidate_count(const mosaic_generator *g, int step, int64_t *first_cell, int64_t *n_cells, int *k)
+{
+    if (!g || step < 0 || step >= (int)g->plans.size() || step >= (int)g->cand_k.size())
+        return MOSAIC_ERR_NOT_READY;
+    if (first_cell)
+        *first_cell = g->plans[step].cell_begin;
+    if (n_cells)
+        *n_cells = g->plans[step].cell_end - g->plans[step].cell_begin;
+    if (k)
+        *k = g->cand_k[step];
+    return MOSAIC_OK;
+}
+
+int mosaic_get_candidates_device(const mosaic_generator *g, int step, void **scores, void **indices)
+{
+    if (!g || step < 0 || step >= (int)g->d_cand_score.size() || !scores || !indices)
+        return MOSAIC_ERR_NOT_READY;
+    *scores = g->d_cand_score[step].p;
+    *indices = g->d_cand_idx[step].p;
+    return MOSAIC_OK;
+}
+
+int mosaic_select_from_candidates(mosaic_generator *g, int step, const void *scores, const void *indices, int k)
+{
+    struct A {
+        int step;
+        const void *scores, *indices;
+        int k;
+    } a{step, scores, indices, k};
+    return guard(g, "selectFromCandidates", [](G *g, void *ap) {
+        A &a = *(A *)ap;
+        if (a.step < 0 || a.step >= (int)g->plans.size() || !a.scores || !a.indices || a.k < 1)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "bad step or candidate buffers"};
+        StepPlan &p = g->plans[a.step];
+        GridStep &gs = g->grid[a.step];
+        cudaStream_t st = g->stream;
+        const int64_t n_all = (int64_t)p.cell_pos.size();
+        for (auto &v : gs.v)
+            v = v >= 0 ? 0 : -1;
+        DevBuf d_grid, d_pos, d_next, d_prog, d_counts;
+        d_grid.alloc(gs.v.size() * sizeof(long long), st);
+        CU(cudaMemcpyAsync(d_grid.p, gs.v.data(), gs.v.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+        d_pos.alloc(std::max<size_t>(p.cell_pos.size(), 1) * sizeof(int), st);
+        CU(cudaMemcpyAsync(d_pos.p, p.cell_pos.data(), p.cell_pos.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        d_next.alloc(std::max<size_t>(p.next_x.size(), 1) * sizeof(int), st);
+        CU(cudaMemcpyAsync(d_next.p, p.next_x.data(), p.next_x.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        d_prog.alloc((size_t)p.rows * sizeof(int), st);
+        CU(cudaMemcpyAsync(d_prog.p, p.row_first.data(), (size_t)p.rows * sizeof(int), cudaMemcpyHostToDevice, st));
+        const int n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_all, select_max_ctas(g->device)));
+        d_counts.alloc((size_t)n_ctas * g->n_lib * sizeof(int), st);
+        CU(cudaMemsetAsync(d_counts.p, 0, d_counts.bytes, st));
+        Timer t(st);
+        t.start();
+        CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols, (const float *)a.scores,
+                         (const int *)a.indices, a.k, a.k, (int)g->n_lib, g->repeat_range, g->repeat_addition, d_prog.as<int>(),
+                         d_counts.as<int>(), n_ctas, nullptr, st));
+        t.stop();
+        CU(cudaMemcpyAsync(gs.v.data(), d_grid.p, gs.v.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        g->timings.select_ms += t.ms();
+        g->timings.kernel_launches += n_all > 0;
+        g->timings.d2h_bytes += (double)(gs.v.size() * sizeof(long long));
+    }, &a);
+}
+
+// ---- host geometry
+
+void mosaic_grid_size(const mosaic_cell_shape *shape, int image_w, int image_h, int pad, int *grid_w, int *grid_h)
+{
+    int gx = 0, gy = 0;
+    grid_size(shape_params_only(*shape), image_w, image_h, pad, gx, gy);
+    *grid_w = gx;
+    *grid_h = gy;
+}
+
+void mosaic_rect_at(const mosaic_cell_shape *shape, int x, int y, int rect_xywh[4])
+{
+    const Rect r = rect_at(shape_params_only(*shape), x, y);
+    rect_xywh[0] = r.x;
+    rect_xywh[1] = r.y;
+    rect_xywh[2] = r.w;
+    rect_xywh[3] = r.h;
+}
+
+int mosaic_flip_at(const mosaic_cell_shape *shape, int x, int y) { return flip_at(shape_params_only(*shape), x, y); }
+
+int mosaic_host_resize_area_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w)
+{
+    if (!src || !dst || cn < 1 || cn > 4)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    return resize_area_u8(src, src_h, src_w, cn, dst, dst_h, dst_w) ? MOSAIC_OK : MOSAIC_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Qt-free, OpenCV-free host model of the reference's domain types on the best-fit path:
+//   CellShape      src/CellShape/CellShape.{h,cpp}   (mask + tiling parameters, resized())
+//   CellGroup      src/CellShape/CellGroup.{h,cpp}   (per size step: normal cell + detail cell)
+//   GridUtility    src/Grid/GridUtility.{h,cpp}      (grid size, cell rect, flip state)
+//   GridGenerator  src/Grid/GridGenerator.{h,cpp}    (valid / split decision per cell), GridBounds
+// plus the OpenCV arithmetic those use on the host (INTER_AREA for 8U, BGR2GRAY, entropy).
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace mm {
+
+constexpr int kPadGrid = 2;  // GridUtility::PAD_GRID, GridUtility.h:33
+
+struct Shape {
+    std::vector<uint8_t> mask;  // size x size, 0 / 255
+    int size = 0;
+    int row_spacing = 0, col_spacing = 0, alt_row_spacing = 0, alt_col_spacing = 0;
+    int alt_row_offset = 0, alt_col_offset = 0;
+    bool alt_col_flip_h = false, alt_col_flip_v = false, alt_row_flip_h = false, alt_row_flip_v = false;
+
+    bool empty() const { return size == 0; }
+    // setCellMask: THRESH_BINARY at 127 (CellShape.cpp:116-135)
+    void set_mask(const uint8_t *m, int s);
+    // the four flipped masks, index = flip_h + 2 * flip_v (CellShape::getCellMask, CellShape.cpp:138-152)
+    std::vector<uint8_t> masks4() const;
+    // CellShape::resized (CellShape.cpp:281-312); false + err when the resize is not supported
+    bool resized(int new_size, Shape &out, std::string &err) const;
+};
+
+struct Group {
+    std::vector<Shape> cells, detail_cells;
+    double detail = 1.0;
+    int size_steps = 0;
+    // CellGroup::setCellShape / setDetail / setSizeSteps (CellGroup.cpp:29-128)
+    bool build(const Shape &top, int detail_percent, int steps, std::string &err);
+};
+
+struct Rect {
+    int x = 0, y = 0, w = 0, h = 0;
+};
+
+void grid_size(const Shape &s, int image_w, int image_h, int pad, int &gx, int &gy);  // GridUtility.cpp:25-52
+Rect rect_at(const Shape &s, int x, int y);                                            // GridUtility.cpp:86-115
+int flip_at(const Shape &s, int x, int y);                                             // GridUtility.cpp:118-132
+
+// getCellAt's bound arithmetic (PhotomosaicGeneratorBase.cpp:296-326): detail-space bound of cell (x, y)
+Rect detail_bound(const Shape &normal, int detail_size, double detail, int x, int y, int image_w, int image_h,
+                  Rect *clamped_global = nullptr, Rect *local = nullptr);
+
+// cv::resize(..., INTER_AREA) for 8U, cn channels, scale >= 1 in both directions (OpenCV's resizeAreaFast_ for
+// integer ratios, resizeArea_ otherwise). Returns false for up-scaling.
+bool resize_area_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw);
+
+// cvtColor(COLOR_BGR2GRAY) for 8U (OpenCV fixed point) and ImageUtility::calculateEntropy (ImageUtility.cpp:189-242)
+void bgr_to_gray_u8(const uint8_t *bgr, size_t n, uint8_t *gray);
+double masked_entropy(const uint8_t *gray, const uint8_t *mask, size_t n);
+
+// GridGenerator::getGridState (GridGenerator.cpp:29-110). grids[step][y * cols + x] = -1 (nullopt) or 0 (valid).
+struct GridStep {
+    int rows = 0, cols = 0;
+    std::vector<int64_t> v;
+};
+bool compute_grid_state(const Group &g, const uint8_t *main_bgr, int rows, int cols, size_t row_stride,
+                        std::vector<GridStep> &out, std::string &err);
+
+}  // namespace mm

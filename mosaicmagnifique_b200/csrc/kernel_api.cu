@@ -1,0 +1,274 @@
+// Kernel-level C entry points (include/mosaic_b200.h, "kernel-level entry points"): the counterparts of the
+// wrapper functions the reference's kernel tests drive
+//   euclideanDifferenceKernelWrapper / CIEDE2000DifferenceKernelWrapper   CUDA/PhotomosaicGenerator.cuh:6-43
+//   reduceAddKernelWrapper                                                CUDA/Reduction.cuh:23
+//   calculateRepeatsKernelWrapper / findLowestKernelWrapper / flattenKernelWrapper
+// Host pointers in, host pointers out; each call runs the SAME kernels the generator uses.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/mosaic_b200.h"
+#include "host_model.h"
+#include "kernels.h"
+
+extern "C" const int16_t mm_lab_lut_s16[];
+
+namespace {
+
+using namespace mm;
+
+struct Dev {
+    void *p = nullptr;
+    ~Dev()
+    {
+        if (p)
+            cudaFree(p);
+    }
+    cudaError_t alloc(size_t n) { return cudaMalloc(&p, std::max<size_t>(n, 16)); }
+    template <typename T>
+    T *as() { return (T *)p; }
+};
+
+#define KCHECK(expr)                  \
+    do {                              \
+        cudaError_t e__ = (expr);     \
+        if (e__ != cudaSuccess) {     \
+            cudaGetLastError();       \
+            return MOSAIC_ERR_CUDA;   \
+        }                             \
+    } while (0)
+
+int use_device(int device)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return MOSAIC_ERR_CUDA;
+    }
+    return cudaSetDevice(device) == cudaSuccess ? MOSAIC_OK : MOSAIC_ERR_CUDA;
+}
+
+// cells: n_cells images [size*size][3] f32 treated as "main images" of their own; lib: n_lib images
+int difference_sums(int type, const float *cells, int n_cells, const float *lib, int64_t n_lib, const uint8_t *mask, int size,
+                    const int32_t *target_area, float *out /* [n_cells][n_lib] */)
+{
+    const int P = size * size;
+    std::vector<int> pix;
+    for (int i = 0; i < P; ++i)
+        if (mask[i])
+            pix.push_back(i);
+    const int n_active = (int)pix.size();
+    const int n_chunks = std::max(1, (n_active + MM_KP - 1) / MM_KP);
+    const int n_lib_tiles = (int)((n_lib + MM_TNB - 1) / MM_TNB), n_lib_pad = n_lib_tiles * MM_TNB;
+    const int n_cell_tiles = (n_cells + MM_TCB - 1) / MM_TCB, n_cells_pad = n_cell_tiles * MM_TCB;
+    const bool chroma = type == MOSAIC_CIEDE2000;
+    std::vector<uint8_t> m4((size_t)4 * P, 0);
+    for (int i = 0; i < P; ++i)
+        m4[i] = mask[i] ? 255 : 0;
+    std::vector<CellDesc> descs(n_cells);
+    for (int c = 0; c < n_cells; ++c) {
+        CellDesc d{0, c * size, 0, 0, size, size, 0, 0};
+        if (target_area) {  // rows [ta0, ta1), cols [ta2, ta3) as in imageDifferenceEdge (PhotomosaicGenerator.cu:53-72)
+            d.by = target_area[0];
+            d.bh = target_area[1] - target_area[0];
+            d.bx = target_area[2];
+            d.bw = target_area[3] - target_area[2];
+        }
+        descs[c] = d;
+    }
+    Dev d_cells, d_lib, d_pix, d_m4, d_desc, d_cp, d_lp, d_D;
+    KCHECK(d_cells.alloc((size_t)n_cells * P * 3 * sizeof(float)));
+    KCHECK(d_lib.alloc((size_t)n_lib * P * 3 * sizeof(float)));
+    KCHECK(d_pix.alloc(pix.size() * sizeof(int)));
+    KCHECK(d_m4.alloc(m4.size()));
+    KCHECK(d_desc.alloc(descs.size() * sizeof(CellDesc)));
+    KCHECK(d_cp.alloc((size_t)n_cell_tiles * n_chunks * (MM_TCB * MM_KP * 20)));
+    KCHECK(d_lp.alloc((size_t)n_lib_tiles * n_chunks * (MM_TNB * MM_KP * 16)));
+    KCHECK(d_D.alloc((size_t)n_cells_pad * n_lib_pad * sizeof(float)));
+    KCHECK(cudaMemcpy(d_cells.p, cells, (size_t)n_cells * P * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_lib.p, lib, (size_t)n_lib * P * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_pix.p, pix.data(), pix.size() * sizeof(int), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_m4.p, m4.data(), m4.size(), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_desc.p, descs.data(), descs.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
+    KCHECK(launch_pack_library(d_lib.as<float>(), d_lp.p, n_lib, P, d_pix.as<int>(), n_active, n_chunks, n_lib_tiles, chroma, 0));
+    // the cells stacked vertically form one "main image" of n_cells*size rows; cell c sits at y0 = c*size; the bound
+    // is relative to the cell, so descs carry by/bx in cell space (extract_cells tests bounds in detail space, k = 1)
+    for (int c = 0; c < n_cells; ++c)
+        descs[c].y0 = c * size;
+    KCHECK(launch_extract_cells(d_cells.as<float>(), n_cells * size, size, d_desc.as<CellDesc>(), n_cells, size, 1, d_m4.as<uint8_t>(),
+                                d_pix.as<int>(), n_active, n_chunks, d_cp.p, chroma, 0));
+    KCHECK(launch_diff_sum(chroma ? MM_DIFF_CIEDE2000 : MM_DIFF_EUCLID, d_cp.p, d_lp.p, d_D.as<float>(), nullptr, n_cell_tiles,
+                           n_lib_tiles, n_chunks, (int)n_lib, n_cells, 0));
+    KCHECK(cudaMemcpy2D(out, (size_t)n_lib * sizeof(float), d_D.p, (size_t)n_lib_pad * sizeof(float), (size_t)n_lib * sizeof(float),
+                        n_cells, cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mosaic_kernel_image_difference_sum(int device, int type, const float *cell, const float *lib, int64_t n_lib, const uint8_t *mask,
+                                       int size, const int32_t *target_area, float *out)
+{
+    if (!cell || !lib || !mask || !out || n_lib <= 0 || size <= 0 || type < 0 || type > 2)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    return difference_sums(type, cell, 1, lib, n_lib, mask, size, target_area, out);
+}
+
+int mosaic_kernel_colour_difference(int device, int type, const float *a, const float *b, int64_t n, float *out)
+{
+    // per-pixel differences = difference sums of 1x1 "images" (the reference's tests call its kernels with size = 1,
+    // tst_ColourDifference.h:233-309): pixel i of a is a cell, pixel i of b its library image.
+    if (!a || !b || !out || n < 0 || type < 0 || type > 2)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (n == 0)
+        return MOSAIC_OK;
+    if (int rc = use_device(device))
+        return rc;
+    const uint8_t mask1 = 255;
+    const int64_t slab = 2048;  // pixels per launch: D is slab x slab floats (16 MB), only its diagonal is kept
+    std::vector<float> D((size_t)slab * slab);
+    for (int64_t s0 = 0; s0 < n; s0 += slab) {
+        const int64_t m = std::min(slab, n - s0);
+        const int rc = difference_sums(type, a + 3 * s0, (int)m, b + 3 * s0, m, &mask1, 1, nullptr, D.data());
+        if (rc)
+            return rc;
+        for (int64_t i = 0; i < m; ++i)
+            out[s0 + i] = D[(size_t)i * m + i];
+    }
+    return MOSAIC_OK;
+}
+
+int mosaic_kernel_select(int device, const float *scores, int64_t n_lib, int64_t *grid, int rows, int cols, int repeat_range,
+                         int repeat_addition)
+{
+    if (!scores || !grid || n_lib <= 0 || rows <= 0 || cols <= 0 || repeat_range < 0 || repeat_addition < 0)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    std::vector<int> pos, next, first(rows, cols);
+    std::vector<long long> g((size_t)rows * cols);
+    for (int y = 0; y < rows; ++y) {
+        int prev = -1;
+        for (int x = 0; x < cols; ++x) {
+            g[(size_t)y * cols + x] = grid[(size_t)y * cols + x] >= 0 ? 0 : -1;
+            if (grid[(size_t)y * cols + x] >= 0) {
+                if (prev < 0)
+                    first[y] = x;
+                else
+                    next[prev] = x;
+                prev = (int)pos.size();
+                pos.push_back(y * cols + x);
+                next.push_back(cols);
+            }
+        }
+    }
+    const int n_cells = (int)pos.size();
+    if (n_cells == 0)
+        return MOSAIC_OK;
+    const int n_ctas = std::max(1, std::min(n_cells, select_max_ctas(device)));
+    Dev d_s, d_g, d_pos, d_next, d_prog, d_cnt;
+    KCHECK(d_s.alloc((size_t)n_cells * n_lib * sizeof(float)));
+    KCHECK(d_g.alloc(g.size() * sizeof(long long)));
+    KCHECK(d_pos.alloc(pos.size() * sizeof(int)));
+    KCHECK(d_next.alloc(next.size() * sizeof(int)));
+    KCHECK(d_prog.alloc((size_t)rows * sizeof(int)));
+    KCHECK(d_cnt.alloc((size_t)n_ctas * n_lib * sizeof(int)));
+    KCHECK(cudaMemcpy(d_s.p, scores, (size_t)n_cells * n_lib * sizeof(float), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_g.p, g.data(), g.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_pos.p, pos.data(), pos.size() * sizeof(int), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_next.p, next.data(), next.size() * sizeof(int), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_prog.p, first.data(), (size_t)rows * sizeof(int), cudaMemcpyHostToDevice));
+    KCHECK(cudaMemset(d_cnt.p, 0, (size_t)n_ctas * n_lib * sizeof(int)));
+    KCHECK(launch_select(d_g.as<long long>(), d_pos.as<int>(), d_next.as<int>(), n_cells, rows, cols, d_s.as<float>(), nullptr, (int)n_lib,
+                         (int)n_lib, (int)n_lib, repeat_range, repeat_addition, d_prog.as<int>(), d_cnt.as<int>(), n_ctas, nullptr, 0));
+    KCHECK(cudaMemcpy(g.data(), d_g.p, g.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < g.size(); ++i)
+        grid[i] = g[i];
+    return MOSAIC_OK;
+}
+
+int mosaic_kernel_topk(int device, const float *scores, int64_t n_rows, int64_t n_lib, int k, float *out_scores, int32_t *out_indices)
+{
+    if (!scores || !out_scores || !out_indices || n_rows <= 0 || n_lib <= 0 || k <= 0 || k > n_lib)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    Dev d_s, d_os, d_oi;
+    KCHECK(d_s.alloc((size_t)n_rows * n_lib * sizeof(float)));
+    KCHECK(d_os.alloc((size_t)n_rows * k * sizeof(float)));
+    KCHECK(d_oi.alloc((size_t)n_rows * k * sizeof(int)));
+    KCHECK(cudaMemcpy(d_s.p, scores, (size_t)n_rows * n_lib * sizeof(float), cudaMemcpyHostToDevice));
+    KCHECK(launch_topk(d_s.as<float>(), (int)n_lib, (int)n_lib, (int)n_rows, k, d_os.as<float>(), d_oi.as<int>(), 0));
+    KCHECK(cudaMemcpy(out_scores, d_os.p, (size_t)n_rows * k * sizeof(float), cudaMemcpyDeviceToHost));
+    KCHECK(cudaMemcpy(out_indices, d_oi.p, (size_t)n_rows * k * sizeof(int), cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
+int mosaic_kernel_bgr_to_lab(int device, const uint8_t *bgr, int64_t n_pixels, float *lab_out)
+{
+    if (!bgr || !lab_out || n_pixels <= 0 || n_pixels > INT32_MAX)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    Dev d_in, d_out, d_lut;
+    KCHECK(d_in.alloc((size_t)n_pixels * 3));
+    KCHECK(d_out.alloc((size_t)n_pixels * 3 * sizeof(float)));
+    KCHECK(d_lut.alloc(33 * 33 * 33 * 3 * sizeof(int16_t)));
+    KCHECK(cudaMemcpy(d_in.p, bgr, (size_t)n_pixels * 3, cudaMemcpyHostToDevice));
+    KCHECK(cudaMemcpy(d_lut.p, mm_lab_lut_s16, 33 * 33 * 33 * 3 * sizeof(int16_t), cudaMemcpyHostToDevice));
+    KCHECK(launch_to_working_space(d_in.as<uint8_t>(), (size_t)n_pixels * 3, 1, (int)n_pixels, d_out.as<float>(), true, d_lut.as<int16_t>(),
+                                   nullptr, 0));
+    KCHECK(cudaMemcpy(lab_out, d_out.p, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
+int mosaic_kernel_resize_area_u8(int device, const uint8_t *src, int64_t n, int size, int k, uint8_t *dst)
+{
+    if (!src || !dst || n <= 0 || size <= 0 || k < 1 || size % k != 0)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    const int ds = size / k;
+    Dev d_in, d_out;
+    KCHECK(d_in.alloc((size_t)n * size * size * 3));
+    KCHECK(d_out.alloc((size_t)n * ds * ds * 3));
+    KCHECK(cudaMemcpy(d_in.p, src, (size_t)n * size * size * 3, cudaMemcpyHostToDevice));
+    KCHECK(launch_area_u8(d_in.as<uint8_t>(), d_out.as<uint8_t>(), n, size, k, 0));
+    KCHECK(cudaMemcpy(dst, d_out.p, (size_t)n * ds * ds * 3, cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
+int mosaic_kernel_resize_area_f32(int device, const float *src, int64_t n, int size, int k, float *dst)
+{
+    if (!src || !dst || n <= 0 || size <= 0 || k < 1 || size % k != 0)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    const int ds = size / k;
+    Dev d_in, d_out;
+    KCHECK(d_in.alloc((size_t)n * size * size * 3 * sizeof(float)));
+    KCHECK(d_out.alloc((size_t)n * ds * ds * 3 * sizeof(float)));
+    KCHECK(cudaMemcpy(d_in.p, src, (size_t)n * size * size * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    KCHECK(launch_area_f32(d_in.as<float>(), d_out.as<float>(), n, size, k, 0));
+    KCHECK(cudaMemcpy(dst, d_out.p, (size_t)n * ds * ds * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
+int mosaic_kernel_microbench(int device, double *out, int n_out)
+{
+    if (!out || n_out < 6)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    KCHECK(run_microbench(out, n_out, 0));
+    return MOSAIC_OK;
+}
+
+}  // extern "C"

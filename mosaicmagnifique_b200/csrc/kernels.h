@@ -1,0 +1,73 @@
+// Internal interface between the host generator (generator.cpp) and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// colour difference types (values of the reference enum, src/Photomosaic/ColourDifference.h:13-19)
+#define MM_DIFF_RGB_EUCLIDEAN 0
+#define MM_DIFF_CIE76 1
+#define MM_DIFF_CIEDE2000 2
+#define MM_DIFF_EUCLID 0  // kernel family used for both RGB_EUCLIDEAN and CIE76
+
+// tile geometry of the packed tensors (see diff_kernels.cu)
+#define MM_TCB 8    // cells per cell tile (= consumer warps per CTA)
+#define MM_TNB 8    // library images per library tile
+#define MM_KP 128   // pixels per chunk
+
+namespace mm {
+
+// ---- diff_kernels.cu
+cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, float *D, unsigned long long *best_key,
+                            int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream);
+
+// ---- prep_kernels.cu
+// u8 BGR -> working space f32 AoS [pixel][3]: Lab through the OpenCV-compatible LUT (is_lab) or a plain cast.
+cudaError_t launch_to_working_space(const uint8_t *bgr, size_t row_stride, int rows, int cols, float *out, bool is_lab,
+                                    const int16_t *lab_lut, const int *c8, cudaStream_t stream);
+// INTER_AREA for integer ratios, 8U 3-channel, batch of n square images (src size s -> dst size s / k)
+cudaError_t launch_area_u8(const uint8_t *src, uint8_t *dst, int64_t n, int src_size, int k, cudaStream_t stream);
+// INTER_AREA for integer ratios, f32 3-channel, batch of n square images
+cudaError_t launch_area_f32(const float *src, float *dst, int64_t n, int src_size, int k, cudaStream_t stream);
+// working f32 AoS library [n][P][3] -> packed float4 tiles (compacted pixel order, chroma in .w)
+cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
+                                int n_chunks, int n_lib_tiles, bool with_chroma, cudaStream_t stream);
+
+struct CellDesc {
+    int x0, y0;          // top-left of the (unclipped) cell rect in main-image space
+    int bx, by, bw, bh;  // detail-space bound
+    int flip;            // mask index: flip_h + 2 * flip_v
+    int variant;         // main-image variant this row compares against
+};
+// main f32 AoS [V][H][W][3] -> packed cell tiles with weights (cell size S -> detail size ds = S / k)
+cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int k,
+                                 const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks, void *packed,
+                                 bool with_chroma, cudaStream_t stream);
+
+// ---- select_kernels.cu
+cudaError_t launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t stream);
+// D rows of V variants -> element-wise minimum into the first variant's rows
+cudaError_t launch_min_variants(float *D, int n_cells, int V, int n_lib_pad, cudaStream_t stream);
+// K smallest (score, index) per row, unsorted. cand_score/cand_idx: [n_cells][K]
+cudaError_t launch_topk(const float *D, int row_stride, int n_lib, int n_cells, int K, float *cand_score, int *cand_idx,
+                        cudaStream_t stream);
+// Repeat-penalised selection in raster order (CPUPhotomosaicGenerator.cpp:81-82, 137-169, 185-225).
+//   grid         : rows x cols int64, in: -1 invalid / >= 0 valid, out: best fit per valid cell
+//   cell_pos     : [n_cells] y * cols + x of each valid cell in raster order (= row order of the scores)
+//   next_x       : [n_cells] column of the next valid cell in the same grid row (cols if none)
+//   scores / idx : per cell M entries; idx == nullptr means "entry j is library image j" (rows of D, stride M_stride)
+//   row_progress : [rows] initialised to the column of the first valid cell of each row (cols if none)
+//   counts       : [n_ctas][n_lib] zero-filled scratch
+cudaError_t launch_select(long long *grid, const int *cell_pos, const int *next_x, int n_cells, int rows, int cols,
+                          const float *scores, const int *idx, int M, int M_stride, int n_lib, int repeat_range,
+                          int repeat_addition, int *row_progress, int *counts, int n_ctas, float *best_score,
+                          cudaStream_t stream);
+int select_max_ctas(int device);
+// best_key (from the diff epilogue) -> grid
+cudaError_t launch_keys_to_grid(const unsigned long long *best_key, const int *cell_pos, long long *grid, int n_cells,
+                                float *best_score, cudaStream_t stream);
+
+// ---- microbench.cu
+// out[0..]: FFMA lane-ops/s, packed FFMA2 lane-ops/s, MUFU rsq ops/s, MUFU ex2 ops/s, sm clock used (Hz, from clock64)
+cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream);
+
+}  // namespace mm

@@ -1,0 +1,158 @@
+// Pipe-rate micro-benchmarks for the roofline denominators MEASURED_PEAKS.json does not carry
+// ("SM count / MUFU width must be confirmed by a micro-benchmark"):
+//   FP32 FFMA lane-ops/s, packed FFMA2 (fma.rn.f32x2) lane-ops/s, MUFU rsq and ex2 ops/s, and the
+//   SM clock that was actually sustained while they ran.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mm {
+
+constexpr int kIters = 4096;
+constexpr int kChains = 16;
+
+__global__ void __launch_bounds__(256) ffma_kernel(float *out, float a, float b, long long *clk)
+{
+    float x[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i)
+        x[i] = (float)(threadIdx.x + i);
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i)
+            x[i] = fmaf(x[i], a, b);
+    }
+    const long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i)
+        s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *clk = t1 - t0;
+}
+
+__global__ void __launch_bounds__(256) ffma2_kernel(float *out, float a, float b, long long *clk)
+{
+    unsigned long long x[kChains / 2];
+    unsigned long long av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int i = 0; i < kChains / 2; ++i) {
+        const float lo = (float)(threadIdx.x + i), hi = lo + 0.5f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x[i]) : "f"(lo), "f"(hi));
+    }
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains / 2; ++i)
+            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[i]) : "l"(av), "l"(bv));
+    }
+    const long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains / 2; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[i]));
+        s += lo + hi;
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *clk = t1 - t0;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) mufu_kernel(float *out, long long *clk)
+{
+    float x[kChains];
+#pragma unroll
+    for (int i = 0; i < kChains; ++i)
+        x[i] = 1.0f + 0.001f * (float)(threadIdx.x + i);
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < kChains; ++i) {
+            if (OP == 0)
+                asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+            else
+                asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < kChains; ++i)
+        s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *clk = t1 - t0;
+}
+
+cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream)
+{
+    if (n_out < 6)
+        return cudaErrorInvalidValue;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    float *buf = nullptr;
+    long long *clk = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)blocks * threads * sizeof(float));
+    if (e != cudaSuccess)
+        return e;
+    e = cudaMalloc(&clk, sizeof(long long));
+    if (e != cudaSuccess) {
+        cudaFree(buf);
+        return e;
+    }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const double lane_ops = (double)blocks * threads * kIters * kChains;
+    for (int which = 0; which < 4; ++which) {
+        float best_ms = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(e0, stream);
+            switch (which) {
+            case 0: ffma_kernel<<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk); break;
+            case 1: ffma2_kernel<<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk); break;
+            case 2: mufu_kernel<0><<<blocks, threads, 0, stream>>>(buf, clk); break;
+            default: mufu_kernel<1><<<blocks, threads, 0, stream>>>(buf, clk); break;
+            }
+            cudaEventRecord(e1, stream);
+            e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess)
+                goto done;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best_ms)
+                best_ms = ms;
+        }
+        out[which] = lane_ops / (best_ms * 1e-3);
+        if (which == 0) {
+            // CTA 0 of an 8-waves-per-SM launch: its loop cycles / (kernel time / 8 waves ... ) is not exact;
+            // report cycles per iteration instead and let the caller combine with nvidia-smi clocks
+            long long c = 0;
+            cudaMemcpyAsync(&c, clk, sizeof c, cudaMemcpyDeviceToHost, stream);
+            cudaStreamSynchronize(stream);
+            out[5] = (double)c / kIters;  // cycles per loop iteration (kChains FFMA per thread, 8 warps/CTA resident mix)
+        }
+    }
+    out[4] = (double)sms;
+
+done:
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(clk);
+    return e;
+}
+
+}  // namespace mm

@@ -1,0 +1,264 @@
+// GPU preprocessing: colour-space conversion, INTER_AREA resizing, cell extraction and packing.
+//
+// Replaces the OpenCV calls of the reference's preprocessing
+//   preprocessMainImage      src/Photomosaic/PhotomosaicGeneratorBase.cpp:223-252
+//   preprocessLibraryImages  src/Photomosaic/PhotomosaicGeneratorBase.cpp:255-290
+//   getCellAt                src/Photomosaic/PhotomosaicGeneratorBase.cpp:293-329
+//   batchResizeMat(lib, .5)  src/Other/ImageUtility.cpp:91-101 (CPUPhotomosaicGenerator.cpp:95-99)
+// bit-exactly with OpenCV's own arithmetic (probed against cv2 4.13, tests/test_prep_parity.py):
+//   * cvtColor(f32, BGR2Lab) is a 33^3 int16 LUT with 4-bit trilinear weights, not the analytic formula;
+//   * INTER_AREA with an integer ratio k sums each k x k block in groups of four in row-major order and
+//     multiplies by float(1/k^2); the 8U version rounds (s+2)>>2 for k == 2 and to nearest-even otherwise.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace mm {
+
+// ------------------------------------------------------------------ BGR8 -> working space
+
+__device__ __forceinline__ int lab_coord(unsigned char v)
+{
+    // convertTo(CV_32F, 1/255.0) multiplies in f32 by float(1/255.0); cvRound(x * LAB_BASE), LAB_BASE = 1 << 14
+    const float f = __fmul_rn((float)v, 0.003921568859368563f);
+    return __float2int_rn(__fmul_rn(f, 16384.0f));
+}
+
+__device__ __forceinline__ void lab_from_bgr8(unsigned char b8, unsigned char g8, unsigned char r8,
+                                              const int16_t *__restrict__ lut, float &L, float &a, float &b)
+{
+    const int cb = lab_coord(b8), cg = lab_coord(g8), cr = lab_coord(r8);
+    const int tb = cb >> 9, tg = cg >> 9, tr = cr >> 9;
+    const int wb = (cb >> 5) & 15, wg = (cg >> 5) & 15, wr = (cr >> 5) & 15;
+    int sL = 0, sa = 0, sb = 0;
+#pragma unroll
+    for (int db = 0; db < 2; ++db)
+#pragma unroll
+        for (int dg = 0; dg < 2; ++dg)
+#pragma unroll
+            for (int dr = 0; dr < 2; ++dr) {
+                const int w = (db ? wb : 16 - wb) * (dg ? wg : 16 - wg) * (dr ? wr : 16 - wr);
+                const int ib = min(tb + db, 32), ig = min(tg + dg, 32), ir = min(tr + dr, 32);
+                const int16_t *e = lut + ((ib * 33 + ig) * 33 + ir) * 3;
+                sL += w * e[0];
+                sa += w * e[1];
+                sb += w * e[2];
+            }
+    const int iL = (sL + 2048) >> 12, ia = (sa + 2048) >> 12, ib2 = (sb + 2048) >> 12;
+    L = __fmul_rn((float)iL * (1.0f / 16384.0f), 100.0f);
+    a = __fadd_rn(__fmul_rn((float)ia * (1.0f / 16384.0f), 256.0f), -128.0f);
+    b = __fadd_rn(__fmul_rn((float)ib2 * (1.0f / 16384.0f), 256.0f), -128.0f);
+}
+
+__global__ void to_working_space_kernel(const uint8_t *__restrict__ bgr, size_t row_stride, int rows, int cols,
+                                        float *__restrict__ out, bool is_lab, const int16_t *__restrict__ lut)
+{
+    const size_t n = (size_t)rows * cols;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t y = i / cols, x = i - y * cols;
+        const uint8_t *p = bgr + y * row_stride + x * 3;
+        float v0, v1, v2;
+        if (is_lab) {
+            lab_from_bgr8(p[0], p[1], p[2], lut, v0, v1, v2);
+        } else {
+            v0 = (float)p[0];
+            v1 = (float)p[1];
+            v2 = (float)p[2];
+        }
+        out[i * 3 + 0] = v0;
+        out[i * 3 + 1] = v1;
+        out[i * 3 + 2] = v2;
+    }
+}
+
+static int grid_for(size_t n, int block)
+{
+    size_t g = (n + block - 1) / block;
+    const size_t cap = 148 * 32;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+cudaError_t launch_to_working_space(const uint8_t *bgr, size_t row_stride, int rows, int cols, float *out, bool is_lab,
+                                    const int16_t *lab_lut, const int *, cudaStream_t stream)
+{
+    const size_t n = (size_t)rows * cols;
+    if (n == 0)
+        return cudaSuccess;
+    to_working_space_kernel<<<grid_for(n, 256), 256, 0, stream>>>(bgr, row_stride, rows, cols, out, is_lab, lab_lut);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ INTER_AREA, integer ratio
+
+__global__ void area_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int64_t n, int S, int k)
+{
+    const int ds = S / k;
+    const size_t total = (size_t)n * ds * ds * 3;
+    const float scale = 1.0f / (float)(k * k);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % 3);
+        size_t t = i / 3;
+        const int dx = (int)(t % ds);
+        t /= ds;
+        const int dy = (int)(t % ds);
+        const size_t im = t / ds;
+        const uint8_t *s = src + (im * S * S + (size_t)(dy * k) * S + (size_t)dx * k) * 3 + ch;
+        int sum = 0;
+        for (int yy = 0; yy < k; ++yy)
+            for (int xx = 0; xx < k; ++xx)
+                sum += s[((size_t)yy * S + xx) * 3];
+        int v;
+        if (k == 2)
+            v = (sum + 2) >> 2;  // OpenCV's SIMD 2x2 path
+        else
+            v = __float2int_rn(__fmul_rn((float)sum, scale));  // saturate_cast<uchar>(sum * scale): cvRound, ties to even
+        dst[i] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+cudaError_t launch_area_u8(const uint8_t *src, uint8_t *dst, int64_t n, int src_size, int k, cudaStream_t stream)
+{
+    const size_t total = (size_t)n * (src_size / k) * (src_size / k) * 3;
+    if (total == 0)
+        return cudaSuccess;
+    area_u8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, n, src_size, k);
+    return cudaGetLastError();
+}
+
+// sum of a k x k block in OpenCV's order: groups of four taps (row-major inside the block) are added
+// left to right and each group total is added to the running sum; the remainder tap by tap.
+template <typename F>
+__device__ __forceinline__ float area_block_f32(int k, F tap)
+{
+    const int area = k * k;
+    float sum = 0.0f;
+    int t = 0;
+    for (; t + 4 <= area; t += 4) {
+        const float g = __fadd_rn(__fadd_rn(__fadd_rn(tap(t), tap(t + 1)), tap(t + 2)), tap(t + 3));
+        sum = __fadd_rn(sum, g);
+    }
+    for (; t < area; ++t)
+        sum = __fadd_rn(sum, tap(t));
+    return __fmul_rn(sum, 1.0f / (float)area);
+}
+
+__global__ void area_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t n, int S, int k)
+{
+    const int ds = S / k;
+    const size_t total = (size_t)n * ds * ds * 3;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % 3);
+        size_t t = i / 3;
+        const int dx = (int)(t % ds);
+        t /= ds;
+        const int dy = (int)(t % ds);
+        const size_t im = t / ds;
+        const float *s = src + (im * S * S + (size_t)(dy * k) * S + (size_t)dx * k) * 3 + ch;
+        dst[i] = area_block_f32(k, [&](int tp) { return s[((size_t)(tp / k) * S + (tp % k)) * 3]; });
+    }
+}
+
+cudaError_t launch_area_f32(const float *src, float *dst, int64_t n, int src_size, int k, cudaStream_t stream)
+{
+    const size_t total = (size_t)n * (src_size / k) * (src_size / k) * 3;
+    if (total == 0)
+        return cudaSuccess;
+    area_f32_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, n, src_size, k);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ packing
+
+__device__ __forceinline__ float chroma_of(float a, float b)
+{
+    // ColourDifference.cpp:48-49 evaluates sqrt(a*a + b*b) in f64 on the f32 pixel values
+    return (float)sqrt((double)a * (double)a + (double)b * (double)b);
+}
+
+__global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
+                                    const int *__restrict__ pix_list, int n_active, int n_chunks, bool with_chroma)
+{
+    // one thread per (image, active pixel)
+    const size_t total = (size_t)n * n_active;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % n_active);
+        const size_t im = i / n_active;
+        const float *s = lib + (im * P + pix_list[q]) * 3;
+        float4 v = make_float4(s[0], s[1], s[2], 0.0f);
+        if (with_chroma)
+            v.w = chroma_of(v.y, v.z);
+        const size_t tile = im / MM_TNB, ti = im % MM_TNB;
+        const int chunk = q / MM_KP, pi = q % MM_KP;
+        float4 *dst = reinterpret_cast<float4 *>(packed + (tile * n_chunks + chunk) * (size_t)(MM_TNB * MM_KP * 16));
+        dst[ti * MM_KP + pi] = v;
+    }
+}
+
+cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
+                                int n_chunks, int n_lib_tiles, bool with_chroma, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_lib_tiles * n_chunks * (MM_TNB * MM_KP * 16), stream);
+    if (e != cudaSuccess)
+        return e;
+    const size_t total = (size_t)n * n_active;
+    if (total == 0)
+        return cudaSuccess;
+    pack_library_kernel<<<grid_for(total, 256), 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active,
+                                                                  n_chunks, with_chroma);
+    return cudaGetLastError();
+}
+
+__global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int W, const CellDesc *__restrict__ cells,
+                                     int n_cells, int S, int k, const uint8_t *__restrict__ masks4,
+                                     const int *__restrict__ pix_list, int n_active, int n_chunks,
+                                     unsigned char *__restrict__ packed, bool with_chroma)
+{
+    const int ds = S / k;
+    const size_t total = (size_t)n_cells * n_active;
+    const size_t block_bytes = (size_t)MM_TCB * MM_KP * 20;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % n_active);
+        const int c = (int)(i / n_active);
+        const CellDesc cd = cells[c];
+        const int p = pix_list[q];
+        const int py = p / ds, px = p - py * ds;
+        const float *img = mains + (size_t)cd.variant * H * W * 3;
+        float v[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            auto tap = [&](int tp) -> float {
+                // zero-filled cell buffer (PhotomosaicGeneratorBase.cpp:310-312): pixels outside the image are 0
+                const int y = cd.y0 + py * k + tp / k, x = cd.x0 + px * k + tp % k;
+                return (y >= 0 && y < H && x >= 0 && x < W) ? img[((size_t)y * W + x) * 3 + ch] : 0.0f;
+            };
+            v[ch] = (k == 1) ? tap(0) : area_block_f32(k, tap);
+        }
+        const bool in_bound = px >= cd.bx && px < cd.bx + cd.bw && py >= cd.by && py < cd.by + cd.bh;
+        const bool active = masks4[((size_t)cd.flip * ds + py) * ds + px] != 0;
+        const size_t tile = c / MM_TCB, ti = c % MM_TCB;
+        const int chunk = q / MM_KP, pi = q % MM_KP;
+        unsigned char *blk = packed + (tile * n_chunks + chunk) * block_bytes;
+        reinterpret_cast<float4 *>(blk)[ti * MM_KP + pi] =
+            make_float4(v[0], v[1], v[2], with_chroma ? chroma_of(v[1], v[2]) : 0.0f);
+        reinterpret_cast<float *>(blk + (size_t)MM_TCB * MM_KP * 16)[ti * MM_KP + pi] = (in_bound && active) ? 1.0f : 0.0f;
+    }
+}
+
+cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int k,
+                                 const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks, void *packed,
+                                 bool with_chroma, cudaStream_t stream)
+{
+    const int n_tiles = (n_cells + MM_TCB - 1) / MM_TCB;
+    cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_tiles * n_chunks * (MM_TCB * MM_KP * 20), stream);
+    if (e != cudaSuccess)
+        return e;
+    const size_t total = (size_t)n_cells * n_active;
+    if (total == 0)
+        return cudaSuccess;
+    extract_cells_kernel<<<grid_for(total, 256), 256, 0, stream>>>(mains, H, W, cells, n_cells, S, k, masks4, pix_list,
+                                                                   n_active, n_chunks, (unsigned char *)packed, with_chroma);
+    return cudaGetLastError();
+}
+
+}  // namespace mm

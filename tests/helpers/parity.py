@@ -1,0 +1,48 @@
+"""Parity criteria shared by the GPU tests (the checker side; imports the oracle).
+
+Grid parity follows the reference's own criterion -- exact equality of the optional-index grid
+(TST_Generator::CompareBestFits, test/tst_Generator.h:25-63) -- with the tie band BASELINE.json allows: a cell may
+differ only if, GIVEN the cells already chosen, its penalised f64 oracle score is within `tol` (relative) of the
+oracle's best score for that cell."""
+import numpy as np
+
+
+def window_counts(grid, x, y, rng_, n_lib):
+    """CPUPhotomosaicGenerator::calculateRepeats (CPUPhotomosaicGenerator.cpp:185-225) occurrence counts."""
+    rows, cols = grid.shape
+    y0 = min(max(y - rng_, 0), rows)
+    x0 = min(max(x - rng_, 0), cols)
+    x1 = min(max(x + rng_, 0), cols - 1)
+    vals = np.concatenate([grid[y0:y, x0:x1 + 1].ravel(), grid[y, x0:x]])
+    vals = vals[vals >= 0]
+    return np.bincount(vals, minlength=n_lib) if vals.size else np.zeros(n_lib, np.int64)
+
+
+def check_grid(D_oracle, grid_state, gpu_grid, repeat_range, repeat_addition, tol=1e-4):
+    """Teacher-forced comparison. Returns (n_cells, n_tie_band, mismatches[list of (y, x, gpu, oracle, rel_gap)])."""
+    rows, cols = grid_state.shape
+    n_lib = D_oracle.shape[1]
+    ties, bad = 0, []
+    c = 0
+    for y in range(rows):
+        for x in range(cols):
+            if grid_state[y, x] < 0:
+                assert gpu_grid[y, x] == -1, "invalid cell %d,%d was filled" % (y, x)
+                continue
+            v = D_oracle[c].astype(np.float64)
+            if repeat_range > 0 and repeat_addition:
+                v = v + repeat_addition * window_counts(gpu_grid, x, y, repeat_range, n_lib)
+            best = int(np.argmin(v))  # first minimum = lowest index, strict < in the reference
+            got = int(gpu_grid[y, x])
+            if got != best:
+                gap = (v[got] - v[best]) / max(v[best], 1e-30) if 0 <= got < n_lib else np.inf
+                if gap <= tol:
+                    ties += 1
+                else:
+                    bad.append((y, x, got, best, float(gap)))
+            c += 1
+    return c, ties, bad
+
+
+def rel_err(D_gpu, D_oracle):
+    return np.abs(D_gpu.astype(np.float64) - D_oracle) / np.maximum(np.abs(D_oracle), 1e-6)

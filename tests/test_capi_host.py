@@ -1,0 +1,111 @@
+"""CPU-side checks of the C ABI: the library loads, exports exactly what include/mosaic_b200.h declares, refuses to
+run without a GPU (no CPU fallback), and its host model (geometry, mask resize) agrees with the oracle / OpenCV."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from mosaicmagnifique_b200 import capi
+    return capi()
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "mosaic_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mosaic_[a-z0-9_]+)\s*\(", text)) - {"mosaic_progress_fn"})
+
+
+def test_library_exports_every_declared_symbol(L):
+    syms = _header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(L, s), "declared in mosaic_b200.h but not exported: " + s
+    assert sorted(L._signatures) == syms, "python binding and header disagree"
+    assert b"sm_100a" in L.mosaic_version()
+
+
+def test_no_cpu_fallback(L):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = ctypes.c_void_p()
+    assert L.mosaic_create(0, ctypes.byref(h)) == -2  # MOSAIC_ERR_CUDA
+    assert not h.value
+    out = np.zeros(8)
+    assert L.mosaic_kernel_microbench(0, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 8) == -2
+
+
+def _shapes(oracle):
+    sq = oracle.CellShape.square(128)
+    hx = oracle.CellShape.square(128)
+    hx.row_spacing, hx.alt_row_spacing, hx.col_spacing, hx.alt_col_spacing, hx.alt_row_offset = 96, 96, 110, 110, 55
+    odd = oracle.CellShape.square(50)
+    odd.row_spacing, odd.alt_row_spacing, odd.col_spacing, odd.alt_col_spacing = 40, 25, 33, 47
+    odd.alt_row_offset, odd.alt_col_offset = 13, 7
+    odd.alt_col_flip_h, odd.alt_row_flip_v, odd.alt_row_flip_h = True, True, True
+    return [sq, hx, odd]
+
+
+def test_geometry_matches_oracle(L, oracle):
+    """GridUtility::calculateGridSize / getRectAt / getFlipStateAt incl. negative coordinates (C++ truncation)."""
+    from mosaicmagnifique_b200._capi import CellShapeC
+    for sh in _shapes(oracle):
+        c = CellShapeC(*sh.params())
+        for (w, h) in ((1920, 1080), (333, 517), (50, 50)):
+            gx, gy = ctypes.c_int(), ctypes.c_int()
+            L.mosaic_grid_size(ctypes.byref(c), w, h, 2, ctypes.byref(gx), ctypes.byref(gy))
+            assert (gx.value, gy.value) == oracle.grid_size(sh, w, h)
+        for y in range(-3, 9):
+            for x in range(-3, 9):
+                r = (ctypes.c_int * 4)()
+                L.mosaic_rect_at(ctypes.byref(c), x, y, r)
+                assert tuple(r) == oracle.rect_at(sh, x, y)
+                assert L.mosaic_flip_at(ctypes.byref(c), x, y) == oracle.flip_at(sh, x, y)
+
+
+def test_oracle_geometry_matches_compiled_reference(oracle):
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_core.so")
+    if not os.path.exists(so):
+        pytest.skip("libref_core.so not built")
+    R = ctypes.CDLL(so)
+    for sh in _shapes(oracle):
+        p = (ctypes.c_int * 11)(*sh.params())
+        for y in range(-3, 9):
+            for x in range(-3, 9):
+                r = (ctypes.c_int * 4)()
+                R.ref_rect_at(p, x, y, r)
+                assert tuple(r) == oracle.rect_at(sh, x, y)
+                assert R.ref_flip_at(p, x, y) == oracle.flip_at(sh, x, y)
+        gx, gy = ctypes.c_int(), ctypes.c_int()
+        R.ref_grid_size(p, 1000, 777, 2, ctypes.byref(gx), ctypes.byref(gy))
+        assert (gx.value, gy.value) == oracle.grid_size(sh, 1000, 777)
+
+
+@pytest.mark.parametrize("src,dst,cn", [(512, 128, 1), (512, 100, 1), (128, 64, 1), (128, 25, 3), (64, 48, 3), (96, 32, 3),
+                                        (100, 37, 1), (64, 64, 1)])
+def test_host_resize_area_matches_opencv(L, src, dst, cn):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(src + dst)
+    a = rng.integers(0, 256, (src, src, cn), dtype=np.uint8)
+    if cn == 1:
+        a = (a > 100).astype(np.uint8) * 255
+    out = np.empty((dst, dst, cn), np.uint8)
+    assert L.mosaic_host_resize_area_u8(a.ctypes.data, src, src, cn, out.ctypes.data, dst, dst) == 0
+    ref = cv2.resize(a, (dst, dst), interpolation=cv2.INTER_AREA).reshape(dst, dst, cn)
+    assert np.array_equal(out, ref)
+
+
+def test_host_resize_area_non_square(L):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 256, (41, 128, 3), dtype=np.uint8)
+    out = np.empty((20, 64, 3), np.uint8)
+    assert L.mosaic_host_resize_area_u8(a.ctypes.data, 41, 128, 3, out.ctypes.data, 20, 64) == 0
+    assert np.array_equal(out, cv2.resize(a, (64, 20), interpolation=cv2.INTER_AREA))

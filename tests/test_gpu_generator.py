@@ -1,0 +1,149 @@
+"""End-to-end parity of the generator on the GPU against the CPU oracle, through the reference-shaped API.
+Option matrix follows the reference's generator tests (test/tst_Generator.h:145-439, tst_CUDAGenerator.h:226-823):
+{RGB, CIE76, CIEDE2000} x {detail 100, 50}, repeats, size steps, a non-square cell shape with flips, edge cells.
+Criterion: grid equality outside the tie band (helpers/parity.py), difference sums within 1e-4 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers.parity import check_grid, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4  # BASELINE.json: per-cell difference values within 1e-4 relative; same number bounds the tie band
+
+
+def _inputs(seed, h, w, n_lib, cell):
+    from mosaicmagnifique_b200 import synthetic
+    return synthetic.make_main_image(h, w, seed, block=32), synthetic.make_library(n_lib, cell, seed + 1)
+
+
+def _oracle_group(oracle, shape, detail, steps):
+    return oracle.CellGroup.make(shape, detail, steps)
+
+
+def _to_product_shape(o_shape):
+    from mosaicmagnifique_b200 import CellShape
+    s = CellShape(o_shape.mask)
+    s.rowSpacing, s.colSpacing = o_shape.row_spacing, o_shape.col_spacing
+    s.alternateRowSpacing, s.alternateColSpacing = o_shape.alt_row_spacing, o_shape.alt_col_spacing
+    s.alternateRowOffset, s.alternateColOffset = o_shape.alt_row_offset, o_shape.alt_col_offset
+    s.alternateColFlipHorizontal, s.alternateColFlipVertical = o_shape.alt_col_flip_h, o_shape.alt_col_flip_v
+    s.alternateRowFlipHorizontal, s.alternateRowFlipVertical = o_shape.alt_row_flip_h, o_shape.alt_row_flip_v
+    return s
+
+
+def _run_case(oracle, main, lib, o_shape, diff, detail, steps, rr, ra, use_oracle_grid_state=True):
+    from mosaicmagnifique_b200 import CellGroup, PhotomosaicGenerator
+    og = _oracle_group(oracle, o_shape, detail, steps)
+    states = oracle.grid_state(og, main)
+    want = oracle.generate(main, lib, og, states, diff, 0, rr, ra, want_D=True)
+
+    gen = PhotomosaicGenerator(0)
+    gen.setMainImage(main)
+    gen.setLibrary(lib)
+    gen.setColourDifference(diff)
+    cg = CellGroup()
+    cg.setCellShape(_to_product_shape(o_shape))
+    cg.setDetail(detail)
+    cg.setSizeSteps(steps)
+    gen.setCellGroup(cg)
+    if use_oracle_grid_state:
+        gen.setGridState(states)
+    else:
+        mine = gen.computeGridState()
+        assert len(mine) == len(states)
+        for a, b in zip(mine, states):
+            assert np.array_equal(a, b)
+    gen.setRepeat(rr, ra)
+    gen.setKeepDifferences(True)
+    assert gen.generateBestFits()
+    got = gen.getBestFits()
+    assert len(got) == len(want)
+    total = ties = 0
+    for step, (g, w) in enumerate(zip(got, want)):
+        D = gen.getDifferences(step)
+        assert D.shape == w.D.shape
+        if D.size:
+            e = rel_err(D, w.D)
+            assert e.max() < TOL, "step %d: max relative error of the difference sums %.3g" % (step, e.max())
+        n, t, bad = check_grid(w.D, states[step], g, rr, ra, TOL)
+        assert not bad, "step %d: %d cells differ outside the tie band, first %s" % (step, len(bad), bad[:3])
+        total += n
+        ties += t
+    tm = gen.getTimings()
+    assert tm["kernel_launches"] > 0
+    assert tm["pixel_diffs"] == sum(w.nominal for w in want)
+    gen.close()
+    return total, ties
+
+
+@pytest.mark.parametrize("diff", [0, 1, 2])
+@pytest.mark.parametrize("detail", [100, 50])
+def test_square_cells(oracle, diff, detail):
+    """CONSISTENCY/COMPARE_{RGB_EUCLIDEAN,CIE76,CIEDE2000}_Detail_{100,50} shape, with repeats as in tst_Generator.h:238."""
+    main, lib = _inputs(11 + diff, 200, 300, 60, 32)
+    total, ties = _run_case(oracle, main, lib, oracle.CellShape.square(32), diff, detail, 0, 3, 10000)
+    assert total == 7 * 10 and ties <= total // 10
+
+
+def test_no_repeats_fused_argmin(oracle):
+    main, lib = _inputs(21, 160, 160, 45, 32)
+    _run_case(oracle, main, lib, oracle.CellShape.square(32), 2, 100, 0, 0, 0)
+
+
+def test_hexagon_like_shape_with_flips_and_edges(oracle):
+    """Config 2 shape: non-square mask, alternate spacing/offsets, flips on odd rows/cols, clipped border cells."""
+    from mosaicmagnifique_b200 import synthetic
+    sh = oracle.CellShape.from_mask(synthetic.triangle_mask(64))
+    sh.row_spacing, sh.alt_row_spacing = 64, 64
+    sh.col_spacing, sh.alt_col_spacing = 32, 32
+    sh.alt_col_flip_v = True
+    sh.alt_row_flip_h = True
+    main, lib = _inputs(31, 230, 310, 50, 32)
+    _run_case(oracle, main, lib, sh.resized(32), 2, 50, 0, 2, 300)
+
+
+def test_hexagon_offsets(oracle):
+    from mosaicmagnifique_b200 import synthetic
+    sh = oracle.CellShape.from_mask(synthetic.hexagon_mask(128))
+    sh.row_spacing, sh.alt_row_spacing = 96, 96   # Hexagon.mcs proportions: rowSp 385/512, colSp 440/512, altRowOffset 220/512
+    sh.col_spacing, sh.alt_col_spacing = 110, 110
+    sh.alt_row_offset = 55
+    main, lib = _inputs(41, 250, 330, 40, 32)
+    _run_case(oracle, main, lib, sh.resized(32), 1, 100, 0, 2, 100)
+
+
+def test_size_steps_with_library_grid_state(oracle):
+    """Config 3 shape: CIE76, 3 size levels (best-fit sub-cell split by the entropy rule), grid state from the library."""
+    main, lib = _inputs(51, 256, 384, 48, 64)
+    total, _ = _run_case(oracle, main, lib, oracle.CellShape.square(64), 1, 100, 2, 2, 200, use_oracle_grid_state=False)
+    assert total > 30
+
+
+def test_mcs_fixture_if_present(oracle):
+    """Cells/Hexagon.mcs of the reference checkout, when it is available (not on the GPU box)."""
+    path = "/root/reference/Cells/Hexagon.mcs"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    sh = oracle.load_mcs(path)
+    main, lib = _inputs(61, 200, 260, 30, 64)
+    _run_case(oracle, main, lib, sh.resized(64), 2, 50, 0, 1, 50)
+
+
+def test_errors_are_reported():
+    from mosaicmagnifique_b200 import CellGroup, CellShape, MosaicError, PhotomosaicGenerator
+    gen = PhotomosaicGenerator(0)
+    with pytest.raises(MosaicError):
+        gen.generateBestFits()  # nothing set
+    with pytest.raises(MosaicError):
+        gen.setColourDifference(7)  # std::invalid_argument in the reference
+    cg = CellGroup()
+    cg.setCellShape(CellShape(16))
+    gen.setCellGroup(cg)
+    gen.setMainImage(np.zeros((40, 40, 3), np.uint8))
+    gen.setLibrary(np.zeros((3, 8, 8, 3), np.uint8))  # wrong size: must be at the cell size
+    gen.computeGridState()
+    with pytest.raises(MosaicError):
+        gen.generateBestFits()
+    gen.close()
