@@ -222,7 +222,7 @@ void mo_cell_bounds(const mo_shape *normal, int detail_size, double detail, int 
 
 /* CPUPhotomosaicGenerator.cpp:185-225. grid is rows x cols of int64 (-1 = nullopt),
  * (x, y) already padded coordinates. Writes (index, penalty) pairs; returns count.
- * ids/pen need room for range*(2*range+1)+range entries. */
+ * ids/pen need room for min(range*(2*range+1)+range, rows*cols) entries. */
 int mo_calculate_repeats(const int64_t *grid, int rows, int cols, int x, int y,
                          int range, int addition, int64_t *ids, int64_t *pen)
 {
@@ -368,9 +368,10 @@ int mo_generate_step(int type, const float *cells, const int *bounds, const int 
                      int early_exit, int y_begin, int y_end, double *D_out, double *margins, mo_stats *stats)
 {
     const int64_t cell_stride = (int64_t)V * dsize * dsize * 3;
-    const int max_rep = range * (2 * range + 1) + range + 1;
-    int64_t *ids = (int64_t *)malloc(sizeof(int64_t) * (size_t)max_rep);
-    int64_t *pen = (int64_t *)malloc(sizeof(int64_t) * (size_t)max_rep);
+    /* distinct images in a window never exceed the number of grid cells (the UI allows ranges up to 100000) */
+    const size_t max_rep = (size_t)rows * (size_t)cols + 1;
+    int64_t *ids = (int64_t *)malloc(sizeof(int64_t) * max_rep);
+    int64_t *pen = (int64_t *)malloc(sizeof(int64_t) * max_rep);
     if (!ids || !pen)
         return -1;
     int64_t vi = 0; /* running index of valid cells */
@@ -405,9 +406,9 @@ int mo_generate_step(int type, const float *cells, const int *bounds, const int 
  * stage in isolation (mirrors test/tst_CUDAKernel.h:20-165). */
 void mo_select_from_D(const double *D, int64_t N, int64_t *grid, int rows, int cols, int range, int addition)
 {
-    const int max_rep = range * (2 * range + 1) + range + 1;
-    int64_t *ids = (int64_t *)malloc(sizeof(int64_t) * (size_t)max_rep);
-    int64_t *pen = (int64_t *)malloc(sizeof(int64_t) * (size_t)max_rep);
+    const size_t max_rep = (size_t)rows * (size_t)cols + 1;
+    int64_t *ids = (int64_t *)malloc(sizeof(int64_t) * max_rep);
+    int64_t *pen = (int64_t *)malloc(sizeof(int64_t) * max_rep);
     int64_t vi = 0;
     for (int y = 0; y < rows; ++y)
         for (int x = 0; x < cols; ++x) {
