@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the photomosaic best-fit path (BASELINE.json config 4).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg4|cfg4-small|...]
+
+Workload (BASELINE.json configs[3], SURVEY.md section 8d "Config 4 (headline)"): synthetic 7680x4320 main image x
+10,000-image library of 128x128 tiles, CIEDE2000, square cells 128, detail 100 %, repeat range 8 / addition 500.
+A "step" is one complete generateBestFits(): preprocessing, the fused difference-sum kernel over cells x library,
+the repeat-penalised wavefront selection, grid back on the host. The same job is sharded by grid rows over N GPUs
+(strong scaling); under torchrun every rank is one process on one GPU.
+
+value  : pixel-differences / second (active, in-bound mask pixels x library images; SURVEY.md 8d metric (i)) with the
+         8-bit inputs already resident in HBM when the timed region starts.
+e2e    : the same metric through the reference-shaped API from pinned HOST buffers each step: setMainImage + setLibrary
+         (H2D) + generateBestFits + getBestFits (D2H).
+The CPU oracle is used here ONLY for the cpu_baseline leg and for --impl reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic work per pixel-difference of the REFERENCE formula
+WORK = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1}, 1: {"flop": 9, "sfu": 1}}
+# what this engine's kernel executes per pixel-difference (colour_math.cuh; instruction counts from SASS / ncu)
+EXECUTED = {2: {"mufu": 11}, 0: {"mufu": 1}, 1: {"mufu": 1}}
+
+WORKLOADS = {
+    # name: (H, W, n_lib, cell, detail, diff, range, addition, seed)
+    "cfg4": dict(h=4320, w=7680, n_lib=10000, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
+                 desc="synthetic 8K (7680x4320) main x 10,000-image library, CIEDE2000, cell 128, detail 100%, repeat 8/500"),
+    "cfg4-d50": dict(h=4320, w=7680, n_lib=10000, cell=128, detail=50, diff=2, rr=8, ra=500, seed=1004,
+                     desc="config 4 at detail 50%"),
+    "cfg4-small": dict(h=1080, w=1920, n_lib=1000, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
+                       desc="config 4 scaled down (1920x1080 x 1,000 images) for quick runs"),
+    "cfg5": dict(h=8640, w=15360, n_lib=20000, cell=128, detail=50, diff=0, rr=0, ra=0, seed=1005,
+                 desc="synthetic 16K main x 20,000-image library, RGB Euclidean, square cells at detail 50%"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm / baseline
+
+def cpu_sample(cfg, main, lib, seconds):
+    """Times the CPU oracle (plain-C restatement of CPUPhotomosaicGenerator, f64, early exit, 1 thread -- the reference
+    generator is single-threaded) on a bounded sample of the workload: the first grid row(s) x a library prefix."""
+    from oracle import oracle
+    og = oracle.CellGroup.make(oracle.CellShape.square(cfg["cell"]), cfg["detail"], 0)
+    n_lib = min(len(lib), 64)
+    sub_lib = lib[:n_lib]
+    t0 = time.perf_counter()
+    state = oracle.grid_state(og, main)[0]
+    mains = [oracle.to_working_space(main, cfg["diff"])]
+    lib_f = oracle.preprocess_library(sub_lib, og, cfg["diff"])
+    cells, bounds, flips, _ = oracle.extract_cells(mains, og, 0, state)
+    masks4 = og.detail_cells[0].masks4()
+    prep_s = time.perf_counter() - t0
+    # calibrate on one grid row, then take as many rows as fit the time budget
+    rows_done, visited, nominal, elapsed = 0, 0, 0, 0.0
+    y = 0
+    while y < state.shape[0] and (rows_done == 0 or elapsed < seconds):
+        if (state[y] >= 0).any():
+            t1 = time.perf_counter()
+            r = oracle.generate_step(cfg["diff"], cells, bounds, flips, lib_f, masks4, state, cfg["rr"], cfg["ra"], want_D=False,
+                                     early_exit=True, y_begin=y, y_end=y + 1)
+            elapsed += time.perf_counter() - t1
+            visited += r.visited
+            nominal += r.nominal
+            rows_done += 1
+        y += 1
+    return {"seconds": elapsed, "prep_seconds": prep_s, "visited": visited, "nominal": nominal, "rows": rows_done, "n_lib": n_lib,
+            "sample": "first %d grid row(s) (%d cells) x first %d library images of the workload, early exit on"
+                      % (rows_done, int(nominal // max(1, n_lib * cfg["cell"] ** 2 * (cfg["detail"] / 100.0) ** 2)), n_lib)}
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(cfg["h"], cfg["w"], cfg["seed"] + 1000)
+    lib = synthetic.make_library(min(cfg["n_lib"], 256), cfg["cell"], cfg["seed"])
+    per_step = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(cfg, main, lib, 0.0)
+    t0 = time.perf_counter()
+    tot_nominal = tot_visited = 0
+    tot_s = 0.0
+    last = None
+    for _ in range(args.steps):
+        last = cpu_sample(cfg, main, lib, per_step)
+        tot_nominal += last["nominal"]
+        tot_visited += last["visited"]
+        tot_s += last["seconds"]
+    wall = time.perf_counter() - t0
+    value = tot_nominal / tot_s
+    out = {"impl": "reference", "metric": "pixel-diffs/sec", "value": value, "unit": "pixel-diffs/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": cfg["desc"], "sample": last["sample"]},
+           "cpu_baseline": {"value": value, "unit": "pixel-diffs/s", "cores": 1, "kind": "port", "sample": last["sample"],
+                            "visited_per_s": tot_visited / tot_s,
+                            "note": "oracle/mosaic_oracle.c (plain-C restatement; the reference needs Qt+OpenCV and cannot be built "
+                                    "here), 1 thread because CPUPhotomosaicGenerator is single-threaded; value counts nominal "
+                                    "pixel-diffs (early exit credited), visited_per_s the differences actually evaluated"},
+           "e2e": {"value": value, "unit": "pixel-diffs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": wall}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------- the B200 arm
+
+def main():
+    args = parse()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator, capi, synthetic
+    from mosaicmagnifique_b200.parallel import generate_sharded
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # synthetic inputs, identical on every rank (seeded), in PINNED host memory for the e2e leg
+    H, W, N, S = cfg["h"], cfg["w"], cfg["n_lib"], cfg["cell"]
+    main_t = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+    lib_t = torch.empty((N, S, S, 3), dtype=torch.uint8).pin_memory()
+    main_np, lib_np = main_t.numpy(), lib_t.numpy()
+    main_np[...] = synthetic.make_main_image(H, W, cfg["seed"] + 1000)
+    synthetic.make_library(N, S, cfg["seed"], out=lib_np)
+
+    gen = PhotomosaicGenerator(local_rank)
+    cg = CellGroup()
+    cg.setCellShape(CellShape(S))
+    cg.setDetail(cfg["detail"])
+    gen.setColourDifference(cfg["diff"])
+    gen.setCellGroup(cg)
+    gen.setRepeat(cfg["rr"], cfg["ra"])
+
+    def load_inputs():
+        gen.setMainImagePtr(main_t.data_ptr(), H, W, W * 3)
+        gen.setLibraryPtr(lib_t.data_ptr(), N, S)
+
+    load_inputs()
+    state = gen.computeGridState()
+    valid_cells = int(sum((s >= 0).sum() for s in state))
+
+    def step():
+        gen.setGridState(state)
+        if world > 1:
+            grids, _ = generate_sharded(gen, rank, world)
+        else:
+            assert gen.generateBestFits()
+            grids = gen.getBestFits()
+        return grids
+
+    # ---- device-resident leg
+    for _ in range(args.warmup):
+        grids = step()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    t0 = time.perf_counter()
+    phase = {"preprocess_ms": 0.0, "diff_ms": 0.0, "select_ms": 0.0}
+    launches = 0
+    for _ in range(args.steps):
+        grids = step()
+        tm = gen.getTimings()
+        for k in phase:
+            phase[k] += tm[k]
+        launches += tm["kernel_launches"]
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clk = clocks.stop()
+    pixel_diffs = tm["pixel_diffs"]          # whole job (every rank counts all cells of the step)
+    local_share = 1.0
+    if world > 1:
+        t = torch.tensor([elapsed, phase["diff_ms"], phase["preprocess_ms"], phase["select_ms"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed, phase["diff_ms"], phase["preprocess_ms"], phase["select_ms"] = t.tolist()
+        info = gen.candidateInfo(0)
+        local_share = info["n_cells"] / max(1, info["n_valid"])
+    ms_per_step = 1e3 * elapsed / args.steps
+    value = pixel_diffs / (elapsed / args.steps)
+
+    # ---- end-to-end leg: pinned host buffers in, grid out, every step
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        load_inputs()
+        grids = step()
+        checksum = int(sum(int(g.sum()) for g in grids))  # touch the D2H result
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_elapsed = t.item()
+    e2e_value = pixel_diffs / (e2e_elapsed / e2e_steps)
+    h2d = int(main_t.numel() + lib_t.numel())
+    d2h = int(sum(g.size * 8 for g in grids))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (diff_sum), live numbers
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    mb = np.zeros(8)
+    import ctypes
+    capi().mosaic_kernel_microbench(local_rank, mb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 8)
+    diff_s = phase["diff_ms"] * 1e-3 / args.steps                  # average duration of the one diff launch per step (CUDA events)
+    units_per_launch = pixel_diffs * local_share                    # pixel-diffs the launch on this GPU processes
+    work = WORK[cfg["diff"]]
+    sfu_rate = work["sfu"] * units_per_launch / diff_s              # reference-formula special-function ops / s
+    flop_rate = work["flop"] * units_per_launch / diff_s
+    ds = int(S * cfg["detail"] / 100)
+    min_bytes = (N * ds * ds * 16 + valid_cells * local_share * ds * ds * 20)  # library + cells read once (packed layout)
+    roofline = {
+        "bound": "mufu", "kernel": "diff_sum_kernel",
+        "achieved": sfu_rate / 1e9, "peak": mb[2] / 1e9, "unit": "Gop/s", "frac": sfu_rate / mb[2],
+        "traffic": None,
+        "note": "SURVEY 8d counts the REFERENCE formula: %d flop + %d special-function ops per pixel-diff; peak = MUFU.RSQ rate "
+                "measured live by the in-library micro-benchmark (16 lanes/clk/SM). The kernel's trig-free CIEDE2000 executes only "
+                "%d MUFU ops per pixel-diff, which is why frac can exceed 1; see executed_*" % (work["flop"], work["sfu"], EXECUTED[cfg["diff"]]["mufu"]),
+        "fp32": {"achieved_tflops": flop_rate / 1e12, "peak_tflops": 2 * mb[1] / 1e12, "frac": flop_rate / (2 * mb[1]),
+                 "peak_source": "live FFMA2 micro-benchmark x 2 flop"},
+        "executed_mufu": {"achieved_gops": EXECUTED[cfg["diff"]]["mufu"] * units_per_launch / diff_s / 1e9, "peak_gops": mb[2] / 1e9,
+                          "frac": EXECUTED[cfg["diff"]]["mufu"] * units_per_launch / diff_s / mb[2]},
+        "hbm": {"min_bytes_per_launch": min_bytes, "achieved_gbs": min_bytes / diff_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                "frac": (min_bytes / diff_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"},
+        "pixel_diffs_per_s_kernel": units_per_launch / diff_s,
+        "reference_formula_ceiling_pixel_diffs_per_s": mb[2] / work["sfu"],
+        "kernel_ms": diff_s * 1e3,
+    }
+
+    out = {"metric": "pixel-diffs/sec", "value": value, "unit": "pixel-diffs/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": cfg["desc"], "name": args.workload, "valid_cells": valid_cells, "library": N, "cell": S,
+                      "detail": cfg["detail"], "colour_difference": ["RGB_EUCLIDEAN", "CIE76", "CIEDE2000"][cfg["diff"]],
+                      "repeat": [cfg["rr"], cfg["ra"]], "pixel_diffs_per_step": pixel_diffs,
+                      "cache": "inputs (%.1f GB packed library + cells per step) exceed the 126 MB L2; nothing is reused across steps"
+                               % (min_bytes / 1e9),
+                      "parallelism": "grid rows sharded over %d GPU(s), library replicated, top-K candidates all-gathered (NCCL)" % world
+                      if world > 1 else "1 GPU"},
+           "generate_ms": ms_per_step,
+           "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+           "e2e": {"value": e2e_value, "unit": "pixel-diffs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1e3 * e2e_elapsed / e2e_steps, "steps": e2e_steps, "result_checksum": checksum},
+           "gpu_launches": int(launches),
+           "clocks": clk, "roofline": roofline,
+           "microbench": {"ffma_lane_ops_per_s": mb[0], "ffma2_lane_ops_per_s": mb[1], "mufu_rsq_per_s": mb[2], "mufu_ex2_per_s": mb[3],
+                          "sm_count": int(mb[4])}}
+
+    if not args.no_cpu_baseline and world == 1:
+        cs = cpu_sample(cfg, main_np, lib_np, args.cpu_seconds)
+        out["cpu_baseline"] = {"value": cs["nominal"] / cs["seconds"], "unit": "pixel-diffs/s", "cores": 1, "kind": "port",
+                               "sample": cs["sample"], "visited_per_s": cs["visited"] / cs["seconds"], "seconds": cs["seconds"]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

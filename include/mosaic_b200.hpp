@@ -1,0 +1,182 @@
+// mosaic_b200.hpp -- header-only C++ mirror of the reference's generator classes over the C ABI (mosaic_b200.h).
+//
+// Same method names, argument meaning and error behaviour as
+//   PhotomosaicGeneratorBase / CUDAPhotomosaicGenerator   src/Photomosaic/PhotomosaicGeneratorBase.h:32-112,
+//                                                          src/Photomosaic/CUDA/CUDAPhotomosaicGenerator.h:27-60
+//   CellShape, CellGroup                                   src/CellShape/CellShape.h, CellGroup.h
+//   GridUtility::MosaicBestFit                             src/Grid/GridUtility.h:29-31
+// so that callers written against the reference (MainWindow.cpp:584-607, tst_Generator.h:66-137,
+// Benchmark_Generator.h:17-81) port mechanically. Qt-free and OpenCV-free: images are described by
+// mosaicb200::Image (pointer + geometry; a cv::Mat maps onto it as {m.data, m.rows, m.cols, m.step}).
+#pragma once
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mosaic_b200.h"
+
+namespace mosaicb200 {
+
+struct Image {  // 8U BGR view
+    const uint8_t *data = nullptr;
+    int rows = 0, cols = 0;
+    size_t step = 0;  // bytes per row
+};
+
+namespace ColourDifference {
+enum class Type { RGB_EUCLIDEAN = 0, CIE76 = 1, CIEDE2000 = 2, MAX };  // ColourDifference.h:13-19
+}
+namespace ColourScheme {
+enum class Type { NONE = 0, COMPLEMENTARY, TRIADIC, COMPOUND, TETRADIC, ANALAGOUS, MAX };  // ColourScheme.h:10-19
+}
+
+namespace GridUtility {
+using CellBestFit = std::optional<size_t>;
+using StepBestFit = std::vector<std::vector<CellBestFit>>;
+using MosaicBestFit = std::vector<StepBestFit>;
+constexpr int PAD_GRID = 2;
+}  // namespace GridUtility
+
+class CellShape {
+public:
+    CellShape() = default;
+    explicit CellShape(size_t size) : m_mask(size * size, 255) { init(static_cast<int>(size)); }  // default square cell
+    CellShape(const uint8_t *mask, int size) : m_mask(mask, mask + static_cast<size_t>(size) * size) { init(size); }
+
+    int getSize() const { return m_c.size; }
+    bool empty() const { return m_mask.empty(); }
+    void setRowSpacing(int v) { m_c.row_spacing = v; }
+    void setColSpacing(int v) { m_c.col_spacing = v; }
+    void setAlternateRowSpacing(int v) { m_c.alt_row_spacing = v; }
+    void setAlternateColSpacing(int v) { m_c.alt_col_spacing = v; }
+    void setAlternateRowOffset(int v) { m_c.alt_row_offset = v; }
+    void setAlternateColOffset(int v) { m_c.alt_col_offset = v; }
+    void setAlternateColFlipHorizontal(bool v) { m_c.alt_col_flip_h = v; }
+    void setAlternateColFlipVertical(bool v) { m_c.alt_col_flip_v = v; }
+    void setAlternateRowFlipHorizontal(bool v) { m_c.alt_row_flip_h = v; }
+    void setAlternateRowFlipVertical(bool v) { m_c.alt_row_flip_v = v; }
+    int getRowSpacing() const { return m_c.row_spacing; }
+    int getColSpacing() const { return m_c.col_spacing; }
+    const std::vector<uint8_t> &getCellMask() const { return m_mask; }
+    const mosaic_cell_shape &c() const { return m_c; }
+
+private:
+    void init(int size)
+    {
+        m_c = mosaic_cell_shape{size, size, size, size, size, 0, 0, 0, 0, 0, 0};
+        for (auto &v : m_mask)
+            v = v > 127 ? 255 : 0;  // setCellMask threshold, CellShape.cpp:123
+    }
+    std::vector<uint8_t> m_mask;
+    mosaic_cell_shape m_c{};
+};
+
+class CellGroup {
+public:
+    void setCellShape(const CellShape &s) { m_shape = s; }
+    const CellShape &getCellShape() const { return m_shape; }
+    void setDetail(int detail = 100) { m_detail = detail; }
+    double getDetail() const { return m_detail / 100.0; }
+    int getDetailPercent() const { return m_detail; }
+    void setSizeSteps(size_t steps) { m_steps = static_cast<int>(steps); }
+    size_t getSizeSteps() const { return static_cast<size_t>(m_steps); }
+
+private:
+    CellShape m_shape;
+    int m_detail = 100, m_steps = 0;
+};
+
+// CUDAPhotomosaicGenerator(const int device): the only back-end; there is no CPU fallback.
+class PhotomosaicGenerator {
+public:
+    explicit PhotomosaicGenerator(int device = 0)
+    {
+        if (mosaic_create(device, &m_g) != MOSAIC_OK)
+            throw std::runtime_error("mosaic_create failed: no usable CUDA device");
+    }
+    ~PhotomosaicGenerator() { mosaic_destroy(m_g); }
+    PhotomosaicGenerator(const PhotomosaicGenerator &) = delete;
+    PhotomosaicGenerator &operator=(const PhotomosaicGenerator &) = delete;
+
+    void setMainImage(const Image &img) { ck(mosaic_set_main_image(m_g, img.data, img.rows, img.cols, img.step)); }
+    // library: n square images of size x size, 8U BGR, contiguous
+    void setLibrary(const uint8_t *bgr, int64_t n, int size) { ck(mosaic_set_library(m_g, bgr, n, size)); }
+    void setColourDifference(ColourDifference::Type t = ColourDifference::Type::RGB_EUCLIDEAN)
+    {
+        if (mosaic_set_colour_difference(m_g, static_cast<int>(t)) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_last_error(m_g));  // ColourDifference.cpp:23
+    }
+    void setColourScheme(ColourScheme::Type t = ColourScheme::Type::NONE)
+    {
+        if (mosaic_set_colour_scheme(m_g, static_cast<int>(t)) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_last_error(m_g));
+    }
+    void setCellGroup(const CellGroup &cg)
+    {
+        m_cells = cg;
+        ck(mosaic_set_cell_group(m_g, &cg.getCellShape().c(), cg.getCellShape().getCellMask().data(), 0, cg.getDetailPercent(),
+                                 static_cast<int>(cg.getSizeSteps())));
+    }
+    CellGroup &getCellGroup() { return m_cells; }
+    void setGridState(const GridUtility::MosaicBestFit &state)
+    {
+        for (size_t s = 0; s < state.size(); ++s) {
+            const int rows = static_cast<int>(state[s].size()), cols = rows ? static_cast<int>(state[s][0].size()) : 0;
+            std::vector<uint8_t> valid(static_cast<size_t>(rows) * cols);
+            for (int y = 0; y < rows; ++y)
+                for (int x = 0; x < cols; ++x)
+                    valid[static_cast<size_t>(y) * cols + x] = state[s][y][x].has_value();
+            ck(mosaic_set_grid_state(m_g, static_cast<int>(s), rows, cols, valid.data()));
+        }
+    }
+    // GridGenerator::getGridState(cellGroup, mainImage, rows, cols) on the inputs already set
+    GridUtility::MosaicBestFit computeGridState()
+    {
+        ck(mosaic_compute_grid_state(m_g));
+        return getBestFits();
+    }
+    void setRepeat(int range = 0, int addition = 0) { ck(mosaic_set_repeat(m_g, range, addition)); }
+
+    // Returns true if successful, false when cancelled or on a CUDA error (text in lastError()), like the reference.
+    bool generateBestFits() { return mosaic_generate(m_g) == MOSAIC_OK; }
+    GridUtility::MosaicBestFit getBestFits() const
+    {
+        GridUtility::MosaicBestFit out(static_cast<size_t>(mosaic_get_grid_steps(m_g)));
+        for (size_t s = 0; s < out.size(); ++s) {
+            int rows = 0, cols = 0;
+            mosaic_get_grid_size(m_g, static_cast<int>(s), &rows, &cols);
+            std::vector<int64_t> v(static_cast<size_t>(rows) * cols);
+            mosaic_get_best_fits(m_g, static_cast<int>(s), v.data(), rows, cols);
+            out[s].assign(rows, std::vector<GridUtility::CellBestFit>(cols));
+            for (int y = 0; y < rows; ++y)
+                for (int x = 0; x < cols; ++x)
+                    if (v[static_cast<size_t>(y) * cols + x] >= 0)
+                        out[s][y][x] = static_cast<size_t>(v[static_cast<size_t>(y) * cols + x]);
+        }
+        return out;
+    }
+    int getMaxProgress() { return mosaic_get_max_progress(m_g); }
+    void cancel() { mosaic_cancel(m_g); }
+    void setProgressCallback(mosaic_progress_fn fn, void *user) { mosaic_set_progress_callback(m_g, fn, user); }
+    std::string lastError() const { return mosaic_last_error(m_g); }
+    mosaic_timings timings() const
+    {
+        mosaic_timings t{};
+        mosaic_get_timings(m_g, &t);
+        return t;
+    }
+    mosaic_generator *handle() { return m_g; }
+
+private:
+    void ck(int rc)
+    {
+        if (rc != MOSAIC_OK)
+            throw std::runtime_error(mosaic_last_error(m_g));
+    }
+    mosaic_generator *m_g = nullptr;
+    CellGroup m_cells;
+};
+
+}  // namespace mosaicb200

@@ -109,3 +109,16 @@ def test_host_resize_area_non_square(L):
     out = np.empty((20, 64, 3), np.uint8)
     assert L.mosaic_host_resize_area_u8(a.ctypes.data, 41, 128, 3, out.ctypes.data, 20, 64) == 0
     assert np.array_equal(out, cv2.resize(a, (64, 20), interpolation=cv2.INTER_AREA))
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    """include/mosaic_b200.hpp (the C++ host mirror of the reference classes) builds against the C ABI; the program
+    itself needs a GPU (exit 3 = clean 'no device' error, 0 = ran)."""
+    import subprocess
+    exe = str(tmp_path / "hpp_check")
+    libdir = os.path.join(ROOT, "mosaicmagnifique_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "helpers", "hpp_compile_check.cpp"),
+                           "-L" + libdir, "-lmosaic_b200", "-Wl,-rpath," + libdir])
+    rc = subprocess.call([exe])
+    import torch
+    assert rc == (0 if torch.cuda.is_available() else 3)
