@@ -42,6 +42,8 @@ WORKLOADS = {
                      desc="config 4 at detail 50%"),
     "cfg4-small": dict(h=1080, w=1920, n_lib=1000, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
                        desc="config 4 scaled down (1920x1080 x 1,000 images) for quick runs"),
+    "cfg4-med": dict(h=2160, w=3840, n_lib=2500, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
+                     desc="config 4 scaled down (3840x2160 x 2,500 images) for kernel tuning"),
     "cfg5": dict(h=8640, w=15360, n_lib=20000, cell=128, detail=50, diff=0, rr=0, ra=0, seed=1005,
                  desc="synthetic 16K main x 20,000-image library, RGB Euclidean, square cells at detail 50%"),
 }

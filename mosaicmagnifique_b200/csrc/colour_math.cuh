@@ -30,7 +30,7 @@
 #include <math.h>
 #include <stdint.h>
 #ifndef __cplusplus
-#include <stdbool.h>
+#error "colour_math.cuh is C++ (the CPU test harness builds it with g++)"
 #endif
 
 #if defined(__CUDACC__)
@@ -46,6 +46,7 @@ MM_HD float mm_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r
 MM_HD float mm_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 MM_HD float mm_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #else
+// CPU emulation for the unit tests (tests/helpers/colour_math_check.cpp); the product never runs this
 MM_HD float mm_rsq(float x) { return 1.0f / sqrtf(x); }
 MM_HD float mm_rcp(float x) { return 1.0f / x; }
 MM_HD float mm_sqrt(float x) { return sqrtf(x); }
@@ -60,126 +61,196 @@ MM_HD float mm_euclid(float x0, float x1, float x2, float y0, float y1, float y2
     return mm_sqrt(fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
 }
 
-// CIEDE2000 (kL = kC = kH = 1). (L, a, b, C) per colour, C = sqrt(a*a + b*b) precomputed per pixel
-// (ColourDifference.cpp:48-49 hoisted out of the pair loop).
-MM_HD float mm_ciede2000(float L1, float a1, float b1, float C1, float L2, float a2, float b2, float C2)
+// ---------------------------------------------------------------------------------------------------
+// Lane vectors: the CIEDE2000 body below is written once, for V = float (one pixel pair) and V = mm_f2 (two pixel
+// pairs: the same cell pixel against two library images). On sm_100a the mm_f2 arithmetic is the packed FP32 pipe
+// (fma/add/mul.rn.f32x2 -> FFMA2 / FADD2 / FMUL2 in SASS): one issue slot for two lanes, which matters because the
+// scalar kernel is issue-bound (profiles/r1_diff_sum_ciede2000_v2.txt). MUFU ops and selects stay per lane.
+// ---------------------------------------------------------------------------------------------------
+struct mm_f2 {
+    float x, y;
+};
+struct mm_b2 {
+    bool x, y;
+};
+
+MM_HD float v_splat(float a, float) { return a; }
+MM_HD mm_f2 v_splat(float a, mm_f2) { return mm_f2{a, a}; }
+
+// ---- scalar lane ops
+MM_HD float v_add(float a, float b) { return a + b; }
+MM_HD float v_mul(float a, float b) { return a * b; }
+MM_HD float v_fma(float a, float b, float c) { return fmaf(a, b, c); }
+MM_HD float v_rsq(float a) { return mm_rsq(a); }
+MM_HD float v_rcp(float a) { return mm_rcp(a); }
+MM_HD float v_sqrt(float a) { return mm_sqrt(a); }
+MM_HD float v_ex2(float a) { return mm_ex2(a); }
+MM_HD bool v_gt0(float a) { return a > 0.0f; }
+MM_HD bool v_eq(float a, float b) { return a == b; }
+MM_HD float v_sel(bool m, float a, float b) { return m ? a : b; }
+MM_HD float v_abs(float a) { return fabsf(a); }
+MM_HD float v_copysign(float a, float s) { return copysignf(a, s); }
+MM_HD float v_min(float a, float b) { return fminf(a, b); }
+MM_HD float v_max(float a, float b) { return fmaxf(a, b); }
+
+// ---- packed lane ops
+#if defined(__CUDA_ARCH__)
+MM_HD mm_f2 v_add(mm_f2 a, mm_f2 b) { const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return mm_f2{r.x, r.y}; }
+MM_HD mm_f2 v_mul(mm_f2 a, mm_f2 b) { const float2 r = __fmul2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return mm_f2{r.x, r.y}; }
+MM_HD mm_f2 v_fma(mm_f2 a, mm_f2 b, mm_f2 c)
 {
+    const float2 r = __ffma2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), make_float2(c.x, c.y));
+    return mm_f2{r.x, r.y};
+}
+#else
+MM_HD mm_f2 v_add(mm_f2 a, mm_f2 b) { return mm_f2{a.x + b.x, a.y + b.y}; }
+MM_HD mm_f2 v_mul(mm_f2 a, mm_f2 b) { return mm_f2{a.x * b.x, a.y * b.y}; }
+MM_HD mm_f2 v_fma(mm_f2 a, mm_f2 b, mm_f2 c) { return mm_f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+#endif
+MM_HD mm_f2 v_rsq(mm_f2 a) { return mm_f2{mm_rsq(a.x), mm_rsq(a.y)}; }
+MM_HD mm_f2 v_rcp(mm_f2 a) { return mm_f2{mm_rcp(a.x), mm_rcp(a.y)}; }
+MM_HD mm_f2 v_sqrt(mm_f2 a) { return mm_f2{mm_sqrt(a.x), mm_sqrt(a.y)}; }
+MM_HD mm_f2 v_ex2(mm_f2 a) { return mm_f2{mm_ex2(a.x), mm_ex2(a.y)}; }
+MM_HD mm_b2 v_gt0(mm_f2 a) { return mm_b2{a.x > 0.0f, a.y > 0.0f}; }
+MM_HD mm_b2 v_eq(mm_f2 a, mm_f2 b) { return mm_b2{a.x == b.x, a.y == b.y}; }
+MM_HD mm_f2 v_sel(mm_b2 m, mm_f2 a, mm_f2 b) { return mm_f2{m.x ? a.x : b.x, m.y ? a.y : b.y}; }
+MM_HD mm_f2 v_abs(mm_f2 a) { return mm_f2{fabsf(a.x), fabsf(a.y)}; }
+MM_HD mm_f2 v_copysign(mm_f2 a, mm_f2 s) { return mm_f2{copysignf(a.x, s.x), copysignf(a.y, s.y)}; }
+MM_HD mm_f2 v_min(mm_f2 a, mm_f2 b) { return mm_f2{fminf(a.x, b.x), fminf(a.y, b.y)}; }
+MM_HD mm_f2 v_max(mm_f2 a, mm_f2 b) { return mm_f2{fmaxf(a.x, b.x), fmaxf(a.y, b.y)}; }
+
+// ---------------------------------------------------------------------------------------------------
+// CIEDE2000 (kL = kC = kH = 1) on HALF-SCALE per-pixel channels, returning dE / 2.
+//
+// Stored per pixel (prep_kernels.cu):  Lh = L/2 - 25,  ah = a/2,  bh = b/2,  Ch = sqrt(a*a + b*b)/2.
+// Everything in the formula that lives in the (a, b) plane is homogeneous of degree one, so half-scale inputs
+// give dC'/2, dH'/2 and (with Lh) dL'/2 and L-bar - 50 for free; the sums C1+C2 ARE the means the formula asks
+// for. The factor 2 goes into the per-pixel weight (w = 2 for an active pixel).
+//
+// Work per pixel pair: 10 MUFU + ~87 FP32 lane-ops (reference: 27 special-function ops in f64). Besides the
+// algebra described at the top of this file:
+//   * T = P4(cos h) + sin h * Q3(cos h): the four cosines of T are Chebyshev polynomials of cos h and sin h times
+//     Chebyshev-U, collected into one quartic and one cubic (8 FMA instead of recurrences);
+//   * mean hue = hue(v1) + dh/2: e^(i dh/2) is (P + dot, cross) for dot > 0 and (|cross|, +-(P - dot)) otherwise
+//     (both well conditioned), rotated by v1 and normalised once;
+//   * dTheta needs only (hbar - 275deg)^2: a quartic in v = 1 - cos(hbar - 275deg) (|error| of the Gaussian < 7e-8);
+//     v is clamped at 1 (|hbar - 275deg| >= 90deg, Gaussian < 2.4e-6); sin(2 dTheta) is an odd polynomial (1.6e-8);
+//   * 1/S_H carries the sqrt(2) of dH' and all constant factors are folded into polynomial coefficients;
+//   * subtractions are written as FMAs with -1 / negated hoisted scalars so that they pack.
+// The first colour (the cell pixel) is scalar and shared by all lanes; the second colour is a lane vector.
+// ---------------------------------------------------------------------------------------------------
+template <typename V>
+MM_HD V mm_ciede2000_half_v(float L1, float a1, float b1, float C1, V L2, V a2, V b2, V C2)
+{
+    const V tag = L2;
+#define K(c) v_splat((c), tag)
     const float k25_7 = 6103515625.0f;  // 25^7, ColourDifference.cpp:46
     const float tiny = 1e-30f;
 
-    // G and a' (:50-57): sqrt(x/(x+k)) = x * rsq(x*(x+k))
-    const float cbar = 0.5f * (C1 + C2);
-    const float cb2 = cbar * cbar;
-    const float cb4 = cb2 * cb2;
-    const float cb7 = cb4 * cb2 * cbar;
-    const float qg = cb7 * mm_rsq(fmaf(cb7, cb7 + k25_7, tiny));
-    const float g1 = fmaf(-0.5f, qg, 1.5f);  // 1 + G
-    const float a1p = g1 * a1, a2p = g1 * a2;
+    // ---- G and a' (:50-57): sqrt(x/(x+k)) = x * rsq(x (x + k))
+    const V cbar = v_add(K(C1), C2);
+    const V cb2 = v_mul(cbar, cbar);
+    const V cb4 = v_mul(cb2, cb2);
+    const V cb7 = v_mul(v_mul(cb4, cb2), cbar);
+    const V qg = v_mul(cb7, v_rsq(v_fma(cb7, v_add(cb7, K(k25_7)), K(tiny))));
+    const V g1 = v_fma(K(-0.5f), qg, K(1.5f));  // 1 + G
+    const V a1p = v_mul(g1, K(a1)), a2p = v_mul(g1, a2);
 
-    // C' (:58-59)
-    const float c1p = mm_sqrt(fmaf(a1p, a1p, b1 * b1));
-    const float c2p = mm_sqrt(fmaf(a2p, a2p, b2 * b2));
+    // ---- C' (:58-59), deltas (:87-89)
+    const V c1p = v_sqrt(v_fma(a1p, a1p, K(b1 * b1)));
+    const V c2p = v_sqrt(v_fma(a2p, a2p, v_mul(b2, b2)));
+    const V dL = v_add(L2, K(-L1));
+    const V dC = v_fma(c1p, K(-1.0f), c2p);
+    const V cpbar = v_add(c1p, c2p);  // true mean C'
 
-    // deltas (:87-102)
-    const float dL = L2 - L1;
-    const float dC = c2p - c1p;
-    const float P = c1p * c2p;
-    const float dot = fmaf(a1p, a2p, b1 * b2);
-    const float cross = fmaf(a1p, b2, -(a2p * b1));
-    const bool pos = dot > 0.0f;
-    const float argA = P + dot;
-    const float argB = 2.0f * (P - dot);
-    const float arg = fmaxf(pos ? argA : argB, tiny);
-    const float rs = mm_rsq(arg);
-    const float dHa = 1.41421356237f * cross * rs;
-    const float dHb = copysignf(arg * rs, cross);
-    float dH = pos ? dHa : dHb;
-    dH = (P == 0.0f) ? 0.0f : dH;  // dh' = 0 when C1'C2' == 0 (:90)
+    // ---- dH' (:90-102) from dot / cross; dHq * sqrt2 = dH'/2
+    const V P = v_fma(c1p, c2p, K(tiny));
+    const V dot = v_fma(a1p, a2p, v_mul(K(b1), b2));
+    const V cross = v_fma(a1p, b2, v_mul(a2p, K(-b1)));
+    const auto pos = v_gt0(dot);
+    const V argA = v_add(P, dot);
+    const V argB = v_fma(dot, K(-1.0f), P);
+    const V rs = v_rsq(v_sel(pos, argA, argB));
+    const V qy = v_sel(pos, cross, v_copysign(argB, cross));
+    const V dHq = v_mul(rs, qy);
 
-    // unit vector of the mean hue (:104-122)
-    float wx = fmaf(c2p, a1p, c1p * a2p);
-    float wy = fmaf(c2p, b1, c1p * b2);
-    if (P == 0.0f) { wx = a1p + a2p; wy = b1 + b2; }  // mean = h1' + h2' with one of them 0 (:109-110)
-    if (argA < 1e-4f * P) {
-        // hues within ~0.8deg of opposite: the sum of the unit vectors cancels. Its direction is also
-        // perp(C2' v1 - C1' v2) signed by the cross product, which stays well conditioned. (Exactly at
-        // 180deg the reference's own mean hue flips with the last bit of atan2, :111-121.)
-        const float dx = fmaf(c2p, a1p, -(c1p * a2p));
-        const float dy = fmaf(c2p, b1, -(c1p * b2));
-        wx = copysignf(1.0f, cross) * -dy;
-        wy = copysignf(1.0f, cross) * dx;
-    }
-    const float n2 = fmaf(wx, wx, wy * wy);
-    const float rn = mm_rsq(fmaxf(n2, tiny));
-    const float ch = wx * rn, sh = wy * rn;
+    // ---- mean hue (:104-122): v1 rotated by dh/2, normalised
+    const V qx = v_sel(pos, argA, v_abs(cross));
+    V mx = v_fma(a1p, qx, v_mul(K(-b1), qy));
+    V my = v_fma(K(b1), qx, v_mul(a1p, qy));
+    const auto achrom = v_eq(P, K(tiny));  // C1'C2' == 0: mean = h1' + h2' with the achromatic one at 0 (:109-110)
+    mx = v_sel(achrom, v_add(a1p, a2p), mx);
+    my = v_sel(achrom, v_add(K(b1), b2), my);
+    const V rn = v_rsq(v_fma(mx, mx, v_fma(my, my, K(tiny))));
+    const V ch = v_mul(mx, rn), sh = v_mul(my, rn);
 
-    // T (:124-127) through angle-addition recurrences
-    const float ch2x = ch + ch;
-    const float c2 = fmaf(ch2x, ch, -1.0f);
-    const float s2 = ch2x * sh;
-    const float c3 = fmaf(ch, c2, -(sh * s2));
-    const float s3 = fmaf(sh, c2, ch * s2);
-    const float c2x2 = c2 + c2;
-    const float c4 = fmaf(c2x2, c2, -1.0f);
-    const float s4 = c2x2 * s2;
-    float T = 1.0f;
-    T = fmaf(-0.17f * 0.86602540378f, ch, T);   // -0.17 cos(h - 30)
-    T = fmaf(-0.17f * 0.5f, sh, T);
-    T = fmaf(0.24f, c2, T);                     // +0.24 cos(2h)
-    T = fmaf(0.32f * 0.99452189536f, c3, T);    // +0.32 cos(3h + 6)
-    T = fmaf(-0.32f * 0.10452846326f, s3, T);
-    T = fmaf(-0.20f * 0.45399049974f, c4, T);   // -0.20 cos(4h - 63)
-    T = fmaf(-0.20f * 0.89100652418f, s4, T);
+    // ---- T (:124-127) as quartic + sin * cubic, pre-scaled by kT so that shn = S_H / sqrt2 = 1/sqrt2 + cpbar * Ts
+    //      a1 = -0.17 cos30, b1 = -0.17 sin30, a2 = 0.24, a3 = 0.32 cos6, b3 = -0.32 sin6, a4 = -0.2 cos63, b4 = -0.2 sin63
+    const float kA1 = -0.17f * 0.86602540378f, kB1 = -0.17f * 0.5f, kA2 = 0.24f, kA3 = 0.32f * 0.99452189536f,
+                kB3 = -0.32f * 0.10452846326f, kA4 = -0.20f * 0.45399049974f, kB4 = -0.20f * 0.89100652418f;
+    const float kT = 0.015f * 0.70710678118f;
+    V tp = K(kT * (8.0f * kA4));
+    tp = v_fma(tp, ch, K(kT * (4.0f * kA3)));
+    tp = v_fma(tp, ch, K(kT * (2.0f * kA2 - 8.0f * kA4)));
+    tp = v_fma(tp, ch, K(kT * (kA1 - 3.0f * kA3)));
+    tp = v_fma(tp, ch, K(kT * (1.0f - kA2 + kA4)));
+    V tq = K(kT * (8.0f * kB4));
+    tq = v_fma(tq, ch, K(kT * (4.0f * kB3)));
+    tq = v_fma(tq, ch, K(kT * (-4.0f * kB4)));
+    tq = v_fma(tq, ch, K(kT * (kB1 - kB3)));
+    const V Ts = v_fma(sh, tq, tp);
+    const V shn = v_fma(cpbar, Ts, K(0.70710678118f));
 
-    // dTheta (:129-134): angle phi = hbar - 275deg from the rotated unit vector
-    const float cphi = fmaf(ch, 0.08715574275f, -(sh * 0.99619469809f));   // cos275 = 0.0871557, sin275 = -0.9961947
-    const float sphi = fmaf(sh, 0.08715574275f, ch * 0.99619469809f);
-    const float th = sphi * mm_rcp(fmaxf(1.0f + cphi, 0.5f));               // tan(phi/2), |.| <= 1 when cphi >= 0
-    const float th2 = th * th;
-    // atan(x)/x on [-1,1] as a degree-6 polynomial in x^2 (Lawson/minimax fit, |err| < 7e-7)
-    float pa = 0.008249403913f;
-    pa = fmaf(pa, th2, -0.03821812122f);
-    pa = fmaf(pa, th2, 0.08530285112f);
-    pa = fmaf(pa, th2, -0.1356754763f);
-    pa = fmaf(pa, th2, 0.1990285901f);
-    pa = fmaf(pa, th2, -0.3332884304f);
-    pa = fmaf(pa, th2, 1.0f);
-    const float half_phi = th * pa;
-    // exp(-(phi/25deg)^2) = 2^(-(4 log2(e) / (25deg)^2) * half_phi^2)
-    const float kexp = -4.0f * 1.44269504089f / (0.43633231299f * 0.43633231299f);
-    float gauss = mm_ex2(kexp * half_phi * half_phi);
-    gauss = (cphi < 0.0f) ? 0.0f : gauss;
-    // sin(2 dTheta), 2 dTheta = (pi/3) * gauss in [0, 1.0472]
-    const float xs = 1.0471975512f * gauss;
-    const float xs2 = xs * xs;
-    float ps = 2.7557319e-6f;
-    ps = fmaf(ps, xs2, -1.9841270e-4f);
-    ps = fmaf(ps, xs2, 8.3333333e-3f);
-    ps = fmaf(ps, xs2, -1.6666667e-1f);
-    ps = fmaf(ps, xs2, 1.0f);
-    const float sin2dt = xs * ps;
+    // ---- dTheta (:129-134): v = 1 - cos(hbar - 275deg); exponent = -(log2 e / (25deg)^2) (hbar - 275deg)^2 = v * poly(v)
+    V v = v_fma(K(0.99619469809f), sh, v_fma(K(-0.08715574275f), ch, K(1.0f)));
+    v = v_min(v, K(1.0f));
+    const float kE = -1.44269504089f / (0.43633231299f * 0.43633231299f);
+    V pe = K(kE * 0.017463532422f);
+    pe = v_fma(pe, v, K(kE * 0.025150421036f));
+    pe = v_fma(pe, v, K(kE * 0.089459953974f));
+    pe = v_fma(pe, v, K(kE * 0.333304633506f));
+    pe = v_fma(pe, v, K(kE * 2.0f));
+    const V gauss = v_ex2(v_mul(pe, v));
+    // -sin(2 dTheta), 2 dTheta = 60deg * gauss: odd polynomial in gauss (|err| < 1.6e-8), sign folded for R_T
+    const V g2 = v_mul(gauss, gauss);
+    V ps = K(2.647660919774267e-4f);
+    ps = v_fma(ps, g2, K(-0.01048760534946101f));
+    ps = v_fma(ps, g2, K(0.19139485959145958f));
+    ps = v_fma(ps, g2, K(-1.0471974082480757f));
+    const V nsin2dt = v_mul(ps, gauss);
 
-    // R_C, R_T (:135-136, 146)
-    const float cpbar = 0.5f * (c1p + c2p);
-    const float cp2 = cpbar * cpbar;
-    const float cp4 = cp2 * cp2;
-    const float cp7 = cp4 * cp2 * cpbar;
-    const float rc = 2.0f * cp7 * mm_rsq(fmaf(cp7, cp7 + k25_7, tiny));
-    const float rt = -sin2dt * rc;
+    // ---- R_C (:135-136): rc2 = 2 sqrt(c^7/(c^7+k)); R_T = -sin(2 dTheta) R_C
+    const V cp2 = v_mul(cpbar, cpbar);
+    const V cp4 = v_mul(cp2, cp2);
+    const V cp7 = v_mul(v_mul(cp4, cp2), cpbar);
+    const V rc2 = v_mul(cp7, v_rsq(v_fma(cp7, v_fma(K(0.25f), cp7, K(0.25f * k25_7)), K(tiny))));
+    const V rt = v_mul(nsin2dt, rc2);
 
-    // S_L, S_C, S_H (:138-144)
-    const float lm = fmaf(0.5f, L1 + L2, -50.0f);
-    const float ql = lm * lm;
-    const float sl = fmaf(0.015f * ql, mm_rsq(20.0f + ql), 1.0f);
-    const float sc = fmaf(0.045f, cpbar, 1.0f);
-    const float shh = fmaf(0.015f * cpbar, T, 1.0f);
+    // ---- S_L, S_C (:138-142); L1 + L2 = Lbar - 50
+    const V lm = v_add(K(L1), L2);
+    const V ql = v_mul(lm, lm);
+    const V sl = v_fma(v_mul(K(0.015f), ql), v_rsq(v_add(ql, K(20.0f))), K(1.0f));
+    const V sc = v_fma(K(0.045f), cpbar, K(1.0f));
 
-    // dE (:153-157), the three divisions share one reciprocal
-    const float scsh = sc * shh;
-    const float inv = mm_rcp(sl * scsh);
-    const float x = dL * (inv * scsh);
-    const float y = dC * (inv * (sl * shh));
-    const float z = dH * (inv * (sl * sc));
-    const float s = fmaf(z, z, fmaf(y, fmaf(rt, z, y), x * x));
-    return mm_sqrt(fmaxf(s, 0.0f));
+    // ---- dE/2 (:153-157): x = dL'/2/S_L, y = dC'/2/S_C, z = dH'/2/S_H = dHq / shn; one shared reciprocal
+    const V scsh = v_mul(sc, shn);
+    const V inv = v_rcp(v_mul(sl, scsh));
+    const V x = v_mul(dL, v_mul(inv, scsh));
+    const V y = v_mul(dC, v_mul(inv, v_mul(sl, shn)));
+    const V z = v_mul(dHq, v_mul(inv, v_mul(sl, sc)));
+    const V s = v_fma(z, z, v_fma(y, v_fma(rt, z, y), v_mul(x, x)));
+    return v_sqrt(v_max(s, K(0.0f)));
+#undef K
+}
+
+MM_HD float mm_ciede2000_half(float L1, float a1, float b1, float C1, float L2, float a2, float b2, float C2)
+{
+    return mm_ciede2000_half_v<float>(L1, a1, b1, C1, L2, a2, b2, C2);
+}
+
+// Full-scale convenience form (tests): (L, a, b, C) per colour, returns dE.
+MM_HD float mm_ciede2000(float L1, float a1, float b1, float C1, float L2, float a2, float b2, float C2)
+{
+    return 2.0f * mm_ciede2000_half(fmaf(0.5f, L1, -25.0f), 0.5f * a1, 0.5f * b1, 0.5f * C1, fmaf(0.5f, L2, -25.0f), 0.5f * a2,
+                                    0.5f * b2, 0.5f * C2);
 }

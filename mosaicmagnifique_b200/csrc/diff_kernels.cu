@@ -9,7 +9,9 @@
 // lowest index wins).
 //
 // Data layout (built by prep_kernels.cu):
-//   lib  : float4 (x0,x1,x2,C)  [lib_tile][chunk][TNB][KP]   one contiguous 16 KB block per (tile, chunk)
+//   lib  : float4 (x0,x1,x2,-)  [lib_tile][chunk][TNB][KP]   one contiguous 16 KB block per (tile, chunk)
+//          CIEDE2000: half-scale channels (L/2-25, a/2, b/2, C/2), w = 2, and image PAIRS interleaved for the packed
+//          FP32 path: [lib_tile][chunk][TNB/2][2][KP] float4 = (L0,L1,a0,a1) then (b0,b1,C0,C1)
 //   cell : float4 (x0,x1,x2,C)  [cell_tile][chunk][TCB][KP]  followed by float w[TCB][KP] -> 20 KB block
 //   w = 1 where the (flipped) detail mask is set and the pixel lies inside the cell's detail-space bound,
 //   else 0; pixels are stored in the compacted order of the step's active-pixel list, padded with w = 0.
@@ -64,15 +66,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
-template <int DIFF>
-__device__ __forceinline__ float pixel_diff(const float4 &c, const float4 &l)
-{
-    if (DIFF == MM_DIFF_CIEDE2000)
-        return mm_ciede2000(c.x, c.y, c.z, c.w, l.x, l.y, l.z, l.w);
-    return mm_euclid(c.x, c.y, c.z, l.x, l.y, l.z);
-}
-
-constexpr int kStages = 3;
+constexpr int kStages = MM_STAGES;
 constexpr int kConsumerWarps = MM_TCB;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr uint32_t kLibBlockBytes = MM_TNB * MM_KP * 16;
@@ -80,7 +74,7 @@ constexpr uint32_t kCellBlockBytes = MM_TCB * MM_KP * 20;
 constexpr uint32_t kStageBytes = kLibBlockBytes + kCellBlockBytes;
 
 template <int DIFF>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, MM_MIN_CTAS)
 diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__restrict__ lib, float *__restrict__ D,
                 unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells)
 {
@@ -135,10 +129,25 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
             const int p = j * 32 + lane;
             const float4 c = cell_s[p];
             const float w = w_s[p];
+            if (DIFF == MM_DIFF_CIEDE2000) {
+                // packed FP32: two library images per lane vector. The tile stores image pairs interleaved:
+                // [pair][0][p] = (L0, L1, a0, a1), [pair][1][p] = (b0, b1, C0, C1)  (prep_kernels.cu)
 #pragma unroll
-            for (int i = 0; i < MM_TNB; ++i) {
-                const float4 l = lib_s[i * MM_KP + p];
-                acc[i] = fmaf(w, pixel_diff<DIFF>(c, l), acc[i]);
+                for (int i = 0; i < MM_TNB / 2; ++i) {
+                    const float4 la = lib_s[(i * 2 + 0) * MM_KP + p];
+                    const float4 lb = lib_s[(i * 2 + 1) * MM_KP + p];
+                    const mm_f2 d = mm_ciede2000_half_v<mm_f2>(c.x, c.y, c.z, c.w, mm_f2{la.x, la.y}, mm_f2{la.z, la.w},
+                                                               mm_f2{lb.x, lb.y}, mm_f2{lb.z, lb.w});
+                    const mm_f2 a2 = v_fma(mm_f2{w, w}, d, mm_f2{acc[2 * i], acc[2 * i + 1]});
+                    acc[2 * i] = a2.x;
+                    acc[2 * i + 1] = a2.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < MM_TNB; ++i) {
+                    const float4 l = lib_s[i * MM_KP + p];
+                    acc[i] = fmaf(w, mm_euclid(c.x, c.y, c.z, l.x, l.y, l.z), acc[i]);
+                }
             }
         }
         __syncwarp();

@@ -41,26 +41,32 @@ struct Fail {
                        std::string(#expr) + ": " + cudaGetErrorString(e__)};                                  \
     } while (0)
 
-// stream-ordered device buffer (cudaMallocAsync pool: reused across generate() calls)
+// Stream-ordered device buffer that keeps its capacity: buffers live in the generator's workspace and are only
+// re-allocated when a call needs more, so a steady-state generate() performs no device allocation at all
+// (the reference allocates and frees everything per call, CUDAPhotomosaicGenerator.cpp:82, 356).
 struct DevBuf {
     void *p = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0, cap = 0;
     cudaStream_t stream = nullptr;
     void alloc(size_t n, cudaStream_t s)
     {
+        if (p && cap >= n) {
+            bytes = n;
+            return;
+        }
         release();
         stream = s;
         if (n == 0)
             return;
         CU(cudaMallocAsync(&p, n, s));
-        bytes = n;
+        bytes = cap = n;
     }
     void release()
     {
         if (p)
             cudaFreeAsync(p, stream);
         p = nullptr;
-        bytes = 0;
+        bytes = cap = 0;
     }
     template <typename T>
     T *as() const { return reinterpret_cast<T *>(p); }
@@ -68,10 +74,10 @@ struct DevBuf {
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), stream(o.stream)
+    DevBuf(DevBuf &&o) noexcept : p(o.p), bytes(o.bytes), cap(o.cap), stream(o.stream)
     {
         o.p = nullptr;
-        o.bytes = 0;
+        o.bytes = o.cap = 0;
     }
     DevBuf &operator=(DevBuf &&o) noexcept
     {
@@ -79,12 +85,20 @@ struct DevBuf {
             release();
             p = o.p;
             bytes = o.bytes;
+            cap = o.cap;
             stream = o.stream;
             o.p = nullptr;
-            o.bytes = 0;
+            o.bytes = o.cap = 0;
         }
         return *this;
     }
+};
+
+// persistent device workspace of one generator (see DevBuf)
+struct Workspace {
+    DevBuf main_f32, lib_small, lib_work, lib_half;
+    DevBuf pix_list, masks4, descs, cells_packed, lib_packed, best_key;
+    DevBuf grid, pos, next, prog, counts;
 };
 
 struct StepPlan {
@@ -129,6 +143,8 @@ struct mosaic_generator {
 
     // products
     DevBuf d_lut;
+    Workspace ws;
+    std::vector<bool> have_D;
     std::vector<StepPlan> plans;
     std::vector<DevBuf> d_D;            // per step [n_local_cells_pad * V][n_lib_pad]
     std::vector<DevBuf> d_cand_score, d_cand_idx;
@@ -329,10 +345,6 @@ void make_plans(G *g)
 
 // ------------------------------------------------------------------ the pipeline
 
-struct StepDev {
-    DevBuf pix_list, masks4, descs, cells_packed, lib_packed, best_key;
-};
-
 void run_pipeline(G *g, bool candidates_only)
 {
     check_ready(g);
@@ -361,14 +373,14 @@ void run_pipeline(G *g, bool candidates_only)
 
     // ---- Preprocess: main image -> working space (PhotomosaicGeneratorBase.cpp:223-252)
     t_pre.start();
-    DevBuf d_main_f32;
+    DevBuf &d_main_f32 = g->ws.main_f32;
     d_main_f32.alloc((size_t)g->img_rows * g->img_cols * 3 * sizeof(float), st);
     CU(launch_to_working_space(g->d_main_u8.as<uint8_t>(), (size_t)g->img_cols * 3, g->img_rows, g->img_cols,
                                d_main_f32.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
     tm.kernel_launches++;
 
     // ---- Preprocess: library -> working space at the detail size of step 0 (:255-290)
-    DevBuf d_lib_work, d_lib_small;
+    DevBuf &d_lib_work = g->ws.lib_work, &d_lib_small = g->ws.lib_small;
     int lib_ds = g->lib_size;
     {
         const uint8_t *src = g->d_lib_u8.as<uint8_t>();
@@ -385,17 +397,19 @@ void run_pipeline(G *g, bool candidates_only)
         CU(launch_to_working_space(src, (size_t)lib_ds * 3, (int)std::min<int64_t>(N * lib_ds, INT32_MAX), lib_ds,
                                    d_lib_work.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
         tm.kernel_launches++;
-        d_lib_small.release();
     }
     t_pre.stop();
     pre_ms += t_pre.ms();
 
-    g->d_D.clear();
-    g->d_D.resize(n_steps);
-    g->d_cand_score.clear();
-    g->d_cand_score.resize(n_steps);
-    g->d_cand_idx.clear();
-    g->d_cand_idx.resize(n_steps);
+    if (g->d_D.size() != n_steps) {
+        g->d_D.clear();
+        g->d_D.resize(n_steps);
+        g->d_cand_score.clear();
+        g->d_cand_score.resize(n_steps);
+        g->d_cand_idx.clear();
+        g->d_cand_idx.resize(n_steps);
+    }
+    g->have_D.assign(n_steps, false);
     g->cand_k.assign(n_steps, 0);
 
     const bool penalise = g->repeat_range > 0 && g->repeat_addition != 0;
@@ -409,17 +423,16 @@ void run_pipeline(G *g, bool candidates_only)
         const Shape &dshape = g->group.detail_cells[s];
         GridStep &gs = g->grid[s];
         const int ds = p.ds, P = ds * ds;
-        StepDev d;
+        Workspace &d = g->ws;
 
         t_pre.start();
         if (s > 0) {
             // halve the working-space library (CPUPhotomosaicGenerator.cpp:95-99)
-            DevBuf half;
+            DevBuf &half = g->ws.lib_half;
             half.alloc((size_t)N * P * 3 * sizeof(float), st);
             CU(launch_area_f32(d_lib_work.as<float>(), half.as<float>(), N, ds * 2, 2, st));
             tm.kernel_launches++;
-            std::swap(d_lib_work.p, half.p);
-            std::swap(d_lib_work.bytes, half.bytes);
+            std::swap(d_lib_work, half);
         }
 
         // active pixel list: union of the four flipped detail masks, raster order
@@ -491,8 +504,10 @@ void run_pipeline(G *g, bool candidates_only)
         const bool fused_argmin = !penalise && V == 1 && !candidates_only && g->world == 1;
         const bool need_D = !fused_argmin || g->keep_D;
         DevBuf &D = g->d_D[s];
-        if (need_D)
+        if (need_D) {
             D.alloc((size_t)std::max(n_rows_pad, 1) * n_lib_pad * sizeof(float), st);
+            g->have_D[s] = true;
+        }
         if (fused_argmin) {
             d.best_key.alloc((size_t)std::max(n_rows_pad, 1) * sizeof(unsigned long long), st);
             CU(launch_fill_u64(d.best_key.as<unsigned long long>(), (size_t)std::max(n_rows_pad, 1), ~0ull, st));
@@ -525,7 +540,7 @@ void run_pipeline(G *g, bool candidates_only)
             if (n_local > 0)
                 tm.kernel_launches++;
         } else {
-            DevBuf d_grid, d_pos, d_next, d_prog, d_counts;
+            DevBuf &d_grid = d.grid, &d_pos = d.pos, &d_next = d.next, &d_prog = d.prog, &d_counts = d.counts;
             d_grid.alloc(gs.v.size() * sizeof(long long), st);
             CU(cudaMemcpyAsync(d_grid.p, gs.v.data(), gs.v.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
             d_pos.alloc(std::max<size_t>(p.cell_pos.size(), 1) * sizeof(int), st);
@@ -555,8 +570,6 @@ void run_pipeline(G *g, bool candidates_only)
         }
         t_sel.stop();
         sel_ms += t_sel.ms();
-        if (!g->keep_D && !candidates_only)
-            D.release();
         CU(cudaStreamSynchronize(st));
 
         // progress(int): the reference emits per cell with weight 4^(steps-1-step) (CPUPhotomosaicGenerator.cpp:55, 87-88)
@@ -617,6 +630,7 @@ void mosaic_destroy(mosaic_generator *g)
     g->d_main_u8.release();
     g->d_lib_u8.release();
     g->d_lut.release();
+    g->ws = Workspace();
     g->d_D.clear();
     g->d_cand_score.clear();
     g->d_cand_idx.clear();
@@ -861,7 +875,7 @@ int64_t mosaic_get_valid_cell_count(const mosaic_generator *g, int step)
 
 int mosaic_get_differences(const mosaic_generator *g, int step, float *out, int64_t n_cells, int64_t n_lib)
 {
-    if (!g || !out || step < 0 || step >= (int)g->d_D.size() || !g->d_D[step].p)
+    if (!g || !out || step < 0 || step >= (int)g->d_D.size() || step >= (int)g->have_D.size() || !g->have_D[step])
         return MOSAIC_ERR_NOT_READY;
     const StepPlan &p = g->plans[step];
     const int64_t n_local = p.cell_end - p.cell_begin;
@@ -944,7 +958,7 @@ int mosaic_select_from_candidates(mosaic_generator *g, int step, const void *sco
         const int64_t n_all = (int64_t)p.cell_pos.size();
         for (auto &v : gs.v)
             v = v >= 0 ? 0 : -1;
-        DevBuf d_grid, d_pos, d_next, d_prog, d_counts;
+        DevBuf &d_grid = g->ws.grid, &d_pos = g->ws.pos, &d_next = g->ws.next, &d_prog = g->ws.prog, &d_counts = g->ws.counts;
         d_grid.alloc(gs.v.size() * sizeof(long long), st);
         CU(cudaMemcpyAsync(d_grid.p, gs.v.data(), gs.v.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
         d_pos.alloc(std::max<size_t>(p.cell_pos.size(), 1) * sizeof(int), st);

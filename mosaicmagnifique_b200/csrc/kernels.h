@@ -12,7 +12,15 @@
 // tile geometry of the packed tensors (see diff_kernels.cu)
 #define MM_TCB 8    // cells per cell tile (= consumer warps per CTA)
 #define MM_TNB 8    // library images per library tile
+#ifndef MM_KP
 #define MM_KP 128   // pixels per chunk
+#endif
+#ifndef MM_STAGES
+#define MM_STAGES 3  // shared-memory ring depth of the difference kernel
+#endif
+#ifndef MM_MIN_CTAS
+#define MM_MIN_CTAS 2  // __launch_bounds__ residency target of the difference kernel
+#endif
 
 namespace mm {
 

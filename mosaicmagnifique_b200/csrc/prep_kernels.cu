@@ -176,6 +176,12 @@ __device__ __forceinline__ float chroma_of(float a, float b)
     return (float)sqrt((double)a * (double)a + (double)b * (double)b);
 }
 
+// CIEDE2000 channels as colour_math.cuh wants them: (L/2 - 25, a/2, b/2, C/2)
+__device__ __forceinline__ float4 half_scale_lab(float L, float a, float b)
+{
+    return make_float4(fmaf(0.5f, L, -25.0f), 0.5f * a, 0.5f * b, 0.5f * chroma_of(a, b));
+}
+
 __global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
                                     const int *__restrict__ pix_list, int n_active, int n_chunks, bool with_chroma)
 {
@@ -187,11 +193,20 @@ __global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char
         const float *s = lib + (im * P + pix_list[q]) * 3;
         float4 v = make_float4(s[0], s[1], s[2], 0.0f);
         if (with_chroma)
-            v.w = chroma_of(v.y, v.z);
+            v = half_scale_lab(v.x, v.y, v.z);
         const size_t tile = im / MM_TNB, ti = im % MM_TNB;
         const int chunk = q / MM_KP, pi = q % MM_KP;
-        float4 *dst = reinterpret_cast<float4 *>(packed + (tile * n_chunks + chunk) * (size_t)(MM_TNB * MM_KP * 16));
-        dst[ti * MM_KP + pi] = v;
+        unsigned char *blk = packed + (tile * n_chunks + chunk) * (size_t)(MM_TNB * MM_KP * 16);
+        if (with_chroma) {
+            // image pairs interleaved for the packed-FP32 kernel: [pair][0][p] = (L0, L1, a0, a1), [pair][1][p] = (b0, b1, C0, C1)
+            float *f = reinterpret_cast<float *>(blk) + ((ti >> 1) * 2 * MM_KP + pi) * 4 + (ti & 1);
+            f[0] = v.x;
+            f[2] = v.y;
+            f[MM_KP * 4 + 0] = v.z;
+            f[MM_KP * 4 + 2] = v.w;
+        } else {
+            reinterpret_cast<float4 *>(blk)[ti * MM_KP + pi] = v;
+        }
     }
 }
 
@@ -240,8 +255,10 @@ __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int
         const int chunk = q / MM_KP, pi = q % MM_KP;
         unsigned char *blk = packed + (tile * n_chunks + chunk) * block_bytes;
         reinterpret_cast<float4 *>(blk)[ti * MM_KP + pi] =
-            make_float4(v[0], v[1], v[2], with_chroma ? chroma_of(v[1], v[2]) : 0.0f);
-        reinterpret_cast<float *>(blk + (size_t)MM_TCB * MM_KP * 16)[ti * MM_KP + pi] = (in_bound && active) ? 1.0f : 0.0f;
+            with_chroma ? half_scale_lab(v[0], v[1], v[2]) : make_float4(v[0], v[1], v[2], 0.0f);
+        // the CIEDE2000 kernel returns dE/2 (half-scale channels): the factor 2 lives in the weight
+        reinterpret_cast<float *>(blk + (size_t)MM_TCB * MM_KP * 16)[ti * MM_KP + pi] =
+            (in_bound && active) ? (with_chroma ? 2.0f : 1.0f) : 0.0f;
     }
 }
 

@@ -18,11 +18,11 @@ def cm():
     out = os.path.join(HERE, "helpers", "_build")
     os.makedirs(out, exist_ok=True)
     so = os.path.join(out, "libcolour_math_check.so")
-    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", so,
-                           os.path.join(HERE, "helpers", "colour_math_check.c"), "-lm"])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so,
+                           os.path.join(HERE, "helpers", "colour_math_check.cpp"), "-lm"])
     L = ctypes.CDLL(so)
     fp = ctypes.POINTER(ctypes.c_float)
-    for f in (L.cm_euclid_batch, L.cm_ciede2000_batch):
+    for f in (L.cm_euclid_batch, L.cm_ciede2000_batch, L.cm_ciede2000_batch_x2):
         f.argtypes = [fp, fp, ctypes.c_long, fp]
 
     def run(fn, a, b):
@@ -31,7 +31,8 @@ def cm():
         o = np.empty(a.shape[0], np.float32)
         fn(a.ctypes.data_as(fp), b.ctypes.data_as(fp), a.shape[0], o.ctypes.data_as(fp))
         return o.astype(np.float64)
-    return {"euclid": lambda a, b: run(L.cm_euclid_batch, a, b), "ciede2000": lambda a, b: run(L.cm_ciede2000_batch, a, b)}
+    return {"euclid": lambda a, b: run(L.cm_euclid_batch, a, b), "ciede2000": lambda a, b: run(L.cm_ciede2000_batch, a, b),
+            "ciede2000_x2": lambda a, b: run(L.cm_ciede2000_batch_x2, a, b)}
 
 
 @pytest.mark.parametrize("name", ["rgb_euclidean", "cie76", "ciede2000"])
@@ -104,3 +105,15 @@ def test_euclid_random_vs_oracle(cm, oracle):
     got = cm["euclid"](a, b)
     want = oracle.diff_batch(0, a, b)
     np.testing.assert_allclose(got, want, rtol=2e-7, atol=1e-6)
+
+
+def test_packed_form_equals_scalar_form(cm):
+    """mm_ciede2000_half_v<mm_f2> (the FFMA2 kernel path: one cell pixel against two library pixels) is the same source as
+    the scalar form; on the CPU both must agree bit for bit."""
+    rng = np.random.default_rng(9)
+    n = 1 << 16
+    a, b = _lab(rng, n), _lab(rng, n)
+    a[1::2] = a[0::2]  # the packed form shares the first colour between its two lanes
+    a[:2000, 1:] = 0
+    b[2000:4000, 1:] = 0
+    assert np.array_equal(cm["ciede2000"](a, b), cm["ciede2000_x2"](a, b))
