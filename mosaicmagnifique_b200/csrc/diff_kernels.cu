@@ -66,6 +66,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  : "memory");
 }
 
+#ifndef MM_PIXEL_UNROLL
+#define MM_PIXEL_UNROLL 1
+#endif
+constexpr int kPixelUnroll = MM_PIXEL_UNROLL;
 constexpr int kStages = MM_STAGES;
 constexpr int kConsumerWarps = MM_TCB;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
@@ -124,7 +128,7 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
         const float4 *lib_s = reinterpret_cast<const float4 *>(smem + (size_t)s * kStageBytes);
         const float4 *cell_s = reinterpret_cast<const float4 *>(smem + (size_t)s * kStageBytes + kLibBlockBytes) + warp * MM_KP;
         const float *w_s = reinterpret_cast<const float *>(smem + (size_t)s * kStageBytes + kLibBlockBytes + MM_TCB * MM_KP * 16) + warp * MM_KP;
-#pragma unroll 1
+#pragma unroll kPixelUnroll
         for (int j = 0; j < MM_KP / 32; ++j) {
             const int p = j * 32 + lane;
             const float4 c = cell_s[p];

@@ -99,6 +99,7 @@ struct Workspace {
     DevBuf main_f32, lib_small, lib_work, lib_half;
     DevBuf pix_list, masks4, descs, cells_packed, lib_packed, best_key;
     DevBuf grid, pos, next, prog, counts;
+    DevBuf tab_start, tab_si, tab_alpha;  // fractional INTER_AREA table of the current step
 };
 
 struct StepPlan {
@@ -301,11 +302,8 @@ void make_plans(G *g)
             throw Fail{MOSAIC_ERR_UNSUPPORTED,
                        "library size and detail mask size disagree at step " + std::to_string(s) +
                            " (the reference reads out of range for this cell size / detail combination)"};
-        if (p.S % p.ds != 0)
-            throw Fail{MOSAIC_ERR_UNSUPPORTED, "detail level must divide the cell size (fractional INTER_AREA for cells is not implemented yet)"};
-        p.k = p.S / p.ds;
-        if (s == 0 && grp.detail != 1.0 && g->lib_size % p.ds != 0)
-            throw Fail{MOSAIC_ERR_UNSUPPORTED, "library detail resize needs an integer ratio"};
+        // integer ratios take OpenCV's resizeAreaFast_ arithmetic, everything else its fractional resizeArea_ (k = 0)
+        p.k = (p.S % p.ds == 0) ? p.S / p.ds : 0;
 
         int gx, gy;
         grid_size(grp.cells[s], g->img_cols, g->img_rows, kPadGrid, gx, gy);
@@ -344,6 +342,21 @@ void make_plans(G *g)
 }
 
 // ------------------------------------------------------------------ the pipeline
+
+AreaTab upload_area_table(G *g, int ssize, int dsize, mosaic_timings &tm)
+{
+    const AreaTable t = make_area_table(ssize, dsize);
+    Workspace &w = g->ws;
+    cudaStream_t st = g->stream;
+    w.tab_start.alloc(t.start.size() * sizeof(int), st);
+    w.tab_si.alloc(t.si.size() * sizeof(int), st);
+    w.tab_alpha.alloc(t.alpha.size() * sizeof(float), st);
+    CU(cudaMemcpyAsync(w.tab_start.p, t.start.data(), t.start.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w.tab_si.p, t.si.data(), t.si.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(w.tab_alpha.p, t.alpha.data(), t.alpha.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    tm.h2d_bytes += (double)((t.start.size() + t.si.size()) * sizeof(int) + t.alpha.size() * sizeof(float));
+    return AreaTab{w.tab_start.as<int>(), w.tab_si.as<int>(), w.tab_alpha.as<float>()};
+}
 
 void run_pipeline(G *g, bool candidates_only)
 {
@@ -385,10 +398,14 @@ void run_pipeline(G *g, bool candidates_only)
     {
         const uint8_t *src = g->d_lib_u8.as<uint8_t>();
         if (g->group.detail != 1.0) {
-            const int k = g->lib_size / g->plans[0].ds;
             lib_ds = g->plans[0].ds;
             d_lib_small.alloc((size_t)N * lib_ds * lib_ds * 3, st);
-            CU(launch_area_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, k, st));
+            if (g->lib_size % lib_ds == 0) {
+                CU(launch_area_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, g->lib_size / lib_ds, st));
+            } else {
+                const AreaTab tab = upload_area_table(g, g->lib_size, lib_ds, tm);
+                CU(launch_area_general_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, lib_ds, tab, st));
+            }
             tm.kernel_launches++;
             src = d_lib_small.as<uint8_t>();
         }
@@ -492,9 +509,12 @@ void run_pipeline(G *g, bool candidates_only)
         CU(cudaMemcpyAsync(d.descs.p, descs.data(), descs.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, st));
         tm.h2d_bytes += (double)(descs.size() * sizeof(CellDesc));
         d.cells_packed.alloc((size_t)std::max(n_cell_tiles, 1) * p.n_chunks * (MM_TCB * MM_KP * 20), st);
-        CU(launch_extract_cells(d_main_f32.as<float>(), g->img_rows, g->img_cols, d.descs.as<CellDesc>(), n_rows_local, p.S, p.k,
-                                d.masks4.as<uint8_t>(), d.pix_list.as<int>(), p.n_active, p.n_chunks, d.cells_packed.p,
-                                with_chroma, st));
+        AreaTab cell_tab{nullptr, nullptr, nullptr};
+        if (p.k == 0)
+            cell_tab = upload_area_table(g, p.S, p.ds, tm);
+        CU(launch_extract_cells(d_main_f32.as<float>(), g->img_rows, g->img_cols, d.descs.as<CellDesc>(), n_rows_local, p.S, p.ds,
+                                p.k, cell_tab, d.masks4.as<uint8_t>(), d.pix_list.as<int>(), p.n_active, p.n_chunks,
+                                d.cells_packed.p, with_chroma, st));
         tm.kernel_launches++;
         t_pre.stop();
         pre_ms += t_pre.ms();

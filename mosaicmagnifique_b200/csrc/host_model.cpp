@@ -46,6 +46,22 @@ inline uint8_t sat_u8(float v)
 
 }  // namespace
 
+AreaTable make_area_table(int ssize, int dsize)
+{
+    AreaTable t;
+    const std::vector<Tap> taps = area_tab(ssize, dsize, 1, (double)ssize / dsize);
+    t.start.assign(dsize + 1, 0);
+    for (const Tap &tp : taps)
+        t.start[tp.di + 1]++;
+    for (int d = 0; d < dsize; ++d)
+        t.start[d + 1] += t.start[d];
+    for (const Tap &tp : taps) {  // taps are already ordered by destination, then source
+        t.si.push_back(tp.si);
+        t.alpha.push_back(tp.alpha);
+    }
+    return t;
+}
+
 bool resize_area_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw)
 {
     if (dh <= 0 || dw <= 0 || sh < dh || sw < dw)

@@ -54,6 +54,14 @@ Rect detail_bound(const Shape &normal, int detail_size, double detail, int x, in
 // integer ratios, resizeArea_ otherwise). Returns false for up-scaling.
 bool resize_area_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw);
 
+// cv::computeResizeAreaTab as a CSR table for the GPU kernels: destination sample d covers source samples
+// si[start[d] .. start[d+1]) with weights alpha (OpenCV's fractional-coverage weights, float)
+struct AreaTable {
+    std::vector<int> start, si;
+    std::vector<float> alpha;
+};
+AreaTable make_area_table(int ssize, int dsize);
+
 // cvtColor(COLOR_BGR2GRAY) for 8U (OpenCV fixed point) and ImageUtility::calculateEntropy (ImageUtility.cpp:189-242)
 void bgr_to_gray_u8(const uint8_t *bgr, size_t n, uint8_t *gray);
 double masked_entropy(const uint8_t *gray, const uint8_t *mask, size_t n);

@@ -98,8 +98,9 @@ int difference_sums(int type, const float *cells, int n_cells, const float *lib,
     // is relative to the cell, so descs carry by/bx in cell space (extract_cells tests bounds in detail space, k = 1)
     for (int c = 0; c < n_cells; ++c)
         descs[c].y0 = c * size;
-    KCHECK(launch_extract_cells(d_cells.as<float>(), n_cells * size, size, d_desc.as<CellDesc>(), n_cells, size, 1, d_m4.as<uint8_t>(),
-                                d_pix.as<int>(), n_active, n_chunks, d_cp.p, chroma, 0));
+    KCHECK(launch_extract_cells(d_cells.as<float>(), n_cells * size, size, d_desc.as<CellDesc>(), n_cells, size, size, 1,
+                                AreaTab{nullptr, nullptr, nullptr}, d_m4.as<uint8_t>(), d_pix.as<int>(), n_active, n_chunks, d_cp.p,
+                                chroma, 0));
     KCHECK(launch_diff_sum(chroma ? MM_DIFF_CIEDE2000 : MM_DIFF_EUCLID, d_cp.p, d_lp.p, d_D.as<float>(), nullptr, n_cell_tiles,
                            n_lib_tiles, n_chunks, (int)n_lib, n_cells, 0));
     KCHECK(cudaMemcpy2D(out, (size_t)n_lib * sizeof(float), d_D.p, (size_t)n_lib_pad * sizeof(float), (size_t)n_lib * sizeof(float),

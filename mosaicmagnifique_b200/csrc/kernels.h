@@ -36,6 +36,16 @@ cudaError_t launch_to_working_space(const uint8_t *bgr, size_t row_stride, int r
 cudaError_t launch_area_u8(const uint8_t *src, uint8_t *dst, int64_t n, int src_size, int k, cudaStream_t stream);
 // INTER_AREA for integer ratios, f32 3-channel, batch of n square images
 cudaError_t launch_area_f32(const float *src, float *dst, int64_t n, int src_size, int k, cudaStream_t stream);
+// INTER_AREA for any down-scaling ratio (OpenCV's resizeArea_): device CSR table of host_model's make_area_table
+struct AreaTab {
+    const int *start;    // [dst_size + 1]
+    const int *si;       // source sample of each tap
+    const float *alpha;  // weight of each tap
+};
+cudaError_t launch_area_general_u8(const uint8_t *src, uint8_t *dst, int64_t n, int src_size, int dst_size, AreaTab tab,
+                                   cudaStream_t stream);
+cudaError_t launch_area_general_f32(const float *src, float *dst, int64_t n, int src_size, int dst_size, AreaTab tab,
+                                    cudaStream_t stream);
 // working f32 AoS library [n][P][3] -> packed float4 tiles (compacted pixel order, chroma in .w)
 cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
                                 int n_chunks, int n_lib_tiles, bool with_chroma, cudaStream_t stream);
@@ -47,9 +57,10 @@ struct CellDesc {
     int variant;         // main-image variant this row compares against
 };
 // main f32 AoS [V][H][W][3] -> packed cell tiles with weights (cell size S -> detail size ds = S / k)
-cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int k,
-                                 const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks, void *packed,
-                                 bool with_chroma, cudaStream_t stream);
+// k > 0: integer ratio S / ds = k; k == 0: fractional ratio through `tab` (detail size ds)
+cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int ds, int k,
+                                 AreaTab tab, const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks,
+                                 void *packed, bool with_chroma, cudaStream_t stream);
 
 // ---- select_kernels.cu
 cudaError_t launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t stream);

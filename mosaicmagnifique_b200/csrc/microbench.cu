@@ -94,6 +94,52 @@ __global__ void __launch_bounds__(256) mufu_kernel(float *out, long long *clk)
         *clk = t1 - t0;
 }
 
+// mixed loop in the CIEDE2000 kernel's proportions: per "pixel pair" 42 packed FP32 ops (84 lane-ops) + 10 MUFU + 10 ALU ops
+template <int N_F2, int N_MUFU, int N_ALU>
+__global__ void __launch_bounds__(256) mixed_kernel(float *out, float a, float b, long long *clk)
+{
+    unsigned long long x[8];
+    float m[4];
+    unsigned long long av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float lo = (float)(threadIdx.x + i), hi = lo + 0.5f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x[i]) : "f"(lo), "f"(hi));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        m[i] = 1.0f + 0.001f * (float)(threadIdx.x + i);
+    float sel = b;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters / 4; ++it) {
+#pragma unroll
+        for (int j = 0; j < N_F2; ++j) {
+            asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[j % 8]) : "l"(av), "l"(bv));
+            if (j * N_MUFU / N_F2 != (j + 1) * N_MUFU / N_F2)
+                asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(m[j % 4]));
+            if (j * N_ALU / N_F2 != (j + 1) * N_ALU / N_F2)
+                asm volatile("max.f32 %0, %0, %1;" : "+f"(sel) : "f"(m[(j + 1) % 4]));
+        }
+    }
+    const long long t1 = clock64();
+    float s = sel;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[i]));
+        s += lo + hi;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        s += m[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *clk = t1 - t0;
+}
+
 cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream)
 {
     if (n_out < 6)
@@ -116,7 +162,9 @@ cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream)
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     const double lane_ops = (double)blocks * threads * kIters * kChains;
-    for (int which = 0; which < 4; ++which) {
+    for (int which = 0; which < 7; ++which) {
+        if (which >= 4 && n_out < 6 + which - 3)
+            break;
         float best_ms = 1e30f;
         for (int rep = 0; rep < 5; ++rep) {
             cudaEventRecord(e0, stream);
@@ -124,7 +172,10 @@ cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream)
             case 0: ffma_kernel<<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk); break;
             case 1: ffma2_kernel<<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk); break;
             case 2: mufu_kernel<0><<<blocks, threads, 0, stream>>>(buf, clk); break;
-            default: mufu_kernel<1><<<blocks, threads, 0, stream>>>(buf, clk); break;
+            case 3: mufu_kernel<1><<<blocks, threads, 0, stream>>>(buf, clk); break;
+            case 4: mixed_kernel<42, 10, 10><<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk); break;
+            case 5: mixed_kernel<42, 10, 0><<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk); break;
+            default: mixed_kernel<42, 0, 0><<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk); break;
             }
             cudaEventRecord(e1, stream);
             e = cudaEventSynchronize(e1);
@@ -134,6 +185,11 @@ cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream)
             cudaEventElapsedTime(&ms, e0, e1);
             if (rep > 0 && ms < best_ms)
                 best_ms = ms;
+        }
+        if (which >= 4) {
+            // "pixel pairs" per second: one inner iteration of mixed_kernel per thread = one pair
+            out[6 + which - 4] = (double)blocks * threads * (kIters / 4) / (best_ms * 1e-3);
+            continue;
         }
         out[which] = lane_ops / (best_ms * 1e-3);
         if (which == 0) {

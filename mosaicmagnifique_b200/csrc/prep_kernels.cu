@@ -168,6 +168,75 @@ cudaError_t launch_area_f32(const float *src, float *dst, int64_t n, int src_siz
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ INTER_AREA, any down-scaling ratio
+// OpenCV's resizeArea_: per source row of the destination row's span, buf = sum_k S[sx_k] * alpha_k accumulated in
+// table order from 0; rows are combined as sum = beta_0 * buf_0, sum += beta_j * buf_j. No FMA contraction.
+template <typename F>
+__device__ __forceinline__ float area_general(const AreaTab &t, int dy, int dx, F tap)
+{
+    float sum = 0.0f;
+    const int y0 = t.start[dy], y1 = t.start[dy + 1];
+    const int x0 = t.start[dx], x1 = t.start[dx + 1];
+    for (int j = y0; j < y1; ++j) {
+        const int sy = t.si[j];
+        float buf = 0.0f;
+        for (int k = x0; k < x1; ++k)
+            buf = __fadd_rn(buf, __fmul_rn(tap(sy, t.si[k]), t.alpha[k]));
+        const float term = __fmul_rn(t.alpha[j], buf);
+        sum = (j == y0) ? term : __fadd_rn(sum, term);
+    }
+    return sum;
+}
+
+__global__ void area_general_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int64_t n, int S, int ds, AreaTab tab)
+{
+    const size_t total = (size_t)n * ds * ds * 3;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % 3);
+        size_t t = i / 3;
+        const int dx = (int)(t % ds);
+        t /= ds;
+        const int dy = (int)(t % ds);
+        const uint8_t *s = src + (t / ds) * (size_t)S * S * 3 + ch;
+        const float v = area_general(tab, dy, dx, [&](int sy, int sx) { return (float)s[((size_t)sy * S + sx) * 3]; });
+        dst[i] = (uint8_t)min(max(__float2int_rn(v), 0), 255);  // saturate_cast<uchar>: cvRound, ties to even
+    }
+}
+
+__global__ void area_general_f32_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t n, int S, int ds, AreaTab tab)
+{
+    const size_t total = (size_t)n * ds * ds * 3;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % 3);
+        size_t t = i / 3;
+        const int dx = (int)(t % ds);
+        t /= ds;
+        const int dy = (int)(t % ds);
+        const float *s = src + (t / ds) * (size_t)S * S * 3 + ch;
+        dst[i] = area_general(tab, dy, dx, [&](int sy, int sx) { return s[((size_t)sy * S + sx) * 3]; });
+    }
+}
+
+cudaError_t launch_area_general_u8(const uint8_t *src, uint8_t *dst, int64_t n, int src_size, int dst_size, AreaTab tab,
+                                   cudaStream_t stream)
+{
+    const size_t total = (size_t)n * dst_size * dst_size * 3;
+    if (total == 0)
+        return cudaSuccess;
+    area_general_u8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, n, src_size, dst_size, tab);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_area_general_f32(const float *src, float *dst, int64_t n, int src_size, int dst_size, AreaTab tab,
+                                    cudaStream_t stream)
+{
+    const size_t total = (size_t)n * dst_size * dst_size * 3;
+    if (total == 0)
+        return cudaSuccess;
+    area_general_f32_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, n, src_size, dst_size, tab);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ packing
 
 __device__ __forceinline__ float chroma_of(float a, float b)
@@ -225,11 +294,10 @@ cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P
 }
 
 __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int W, const CellDesc *__restrict__ cells,
-                                     int n_cells, int S, int k, const uint8_t *__restrict__ masks4,
+                                     int n_cells, int S, int ds, int k, AreaTab tab, const uint8_t *__restrict__ masks4,
                                      const int *__restrict__ pix_list, int n_active, int n_chunks,
                                      unsigned char *__restrict__ packed, bool with_chroma)
 {
-    const int ds = S / k;
     const size_t total = (size_t)n_cells * n_active;
     const size_t block_bytes = (size_t)MM_TCB * MM_KP * 20;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -247,7 +315,11 @@ __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int
                 const int y = cd.y0 + py * k + tp / k, x = cd.x0 + px * k + tp % k;
                 return (y >= 0 && y < H && x >= 0 && x < W) ? img[((size_t)y * W + x) * 3 + ch] : 0.0f;
             };
-            v[ch] = (k == 1) ? tap(0) : area_block_f32(k, tap);
+            auto tap2 = [&](int sy, int sx) -> float {
+                const int y = cd.y0 + sy, x = cd.x0 + sx;
+                return (y >= 0 && y < H && x >= 0 && x < W) ? img[((size_t)y * W + x) * 3 + ch] : 0.0f;
+            };
+            v[ch] = (k == 1) ? tap(0) : (k > 1 ? area_block_f32(k, tap) : area_general(tab, py, px, tap2));
         }
         const bool in_bound = px >= cd.bx && px < cd.bx + cd.bw && py >= cd.by && py < cd.by + cd.bh;
         const bool active = masks4[((size_t)cd.flip * ds + py) * ds + px] != 0;
@@ -262,9 +334,9 @@ __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int
     }
 }
 
-cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int k,
-                                 const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks, void *packed,
-                                 bool with_chroma, cudaStream_t stream)
+cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int ds, int k,
+                                 AreaTab tab, const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks,
+                                 void *packed, bool with_chroma, cudaStream_t stream)
 {
     const int n_tiles = (n_cells + MM_TCB - 1) / MM_TCB;
     cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_tiles * n_chunks * (MM_TCB * MM_KP * 20), stream);
@@ -273,7 +345,7 @@ cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDes
     const size_t total = (size_t)n_cells * n_active;
     if (total == 0)
         return cudaSuccess;
-    extract_cells_kernel<<<grid_for(total, 256), 256, 0, stream>>>(mains, H, W, cells, n_cells, S, k, masks4, pix_list,
+    extract_cells_kernel<<<grid_for(total, 256), 256, 0, stream>>>(mains, H, W, cells, n_cells, S, ds, k, tab, masks4, pix_list,
                                                                    n_active, n_chunks, (unsigned char *)packed, with_chroma);
     return cudaGetLastError();
 }

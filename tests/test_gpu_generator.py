@@ -147,3 +147,11 @@ def test_errors_are_reported():
     with pytest.raises(MosaicError):
         gen.generateBestFits()
     gen.close()
+
+
+@pytest.mark.parametrize("diff,cell,detail", [(2, 32, 30), (0, 50, 75), (1, 40, 33)])
+def test_fractional_detail(oracle, diff, cell, detail):
+    """Detail levels that do not divide the cell size (the reference's benchmark default is 20 %, Benchmark_Generator.h:125):
+    OpenCV's fractional INTER_AREA on the 8U library and on the f32 cells, reproduced on the GPU."""
+    main, lib = _inputs(81 + diff, 210, 290, 40, cell)
+    _run_case(oracle, main, lib, oracle.CellShape.square(cell), diff, detail, 0, 2, 150)
