@@ -151,6 +151,8 @@ int mosaic_kernel_topk(int device, const float *scores, int64_t n_rows, int64_t 
                        int32_t *out_indices);
 /* OpenCV-compatible preprocessing pieces */
 int mosaic_kernel_bgr_to_lab(int device, const uint8_t *bgr, int64_t n_pixels, float *lab_out);
+/* one hue-rotated colour-scheme variant: 8U BGR -> HSV_FULL (f32) -> H = fmod(H + rotation, 360) -> BGR -> 8U (ColourScheme.cpp:36-177) */
+int mosaic_kernel_hue_rotate(int device, const uint8_t *bgr, int rows, int cols, float rotation_degrees, uint8_t *out);
 int mosaic_kernel_resize_area_u8(int device, const uint8_t *src, int64_t n, int size, int k, uint8_t *dst);
 int mosaic_kernel_resize_area_f32(int device, const float *src, int64_t n, int size, int k, float *dst);
 /* FP32 / MUFU pipe-rate micro-benchmark (roofline denominators): out[0] FFMA lane-ops/s, [1] FFMA2 lane-ops/s,

@@ -83,6 +83,7 @@ def capi():
         "mosaic_kernel_select": (i, [i, vp, i64, vp, i, i, i, i]),
         "mosaic_kernel_topk": (i, [i, vp, i64, i64, i, vp, vp]),
         "mosaic_kernel_bgr_to_lab": (i, [i, vp, i64, vp]),
+        "mosaic_kernel_hue_rotate": (i, [i, vp, i, i, c.c_float, vp]),
         "mosaic_kernel_resize_area_u8": (i, [i, vp, i64, i, i, vp]),
         "mosaic_kernel_resize_area_f32": (i, [i, vp, i64, i, i, vp]),
         "mosaic_kernel_microbench": (i, [i, dblp, i]),

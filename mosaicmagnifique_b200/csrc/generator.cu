@@ -96,7 +96,7 @@ struct DevBuf {
 
 // persistent device workspace of one generator (see DevBuf)
 struct Workspace {
-    DevBuf main_f32, lib_small, lib_work, lib_half;
+    DevBuf main_f32, main_var_u8, lib_small, lib_work, lib_half;
     DevBuf pix_list, masks4, descs, cells_packed, lib_packed, best_key;
     DevBuf grid, pos, next, prog, counts;
     DevBuf tab_start, tab_si, tab_alpha;  // fractional INTER_AREA table of the current step
@@ -273,8 +273,6 @@ void check_ready(G *g)
     if (g->lib_size != g->group.cells[0].size)
         throw Fail{MOSAIC_ERR_INVALID_ARGUMENT,
                    "library images must be at the cell size (the reference resizes them before setLibrary, MainWindow.cpp:575-581)"};
-    if (g->scheme != MOSAIC_SCHEME_NONE)
-        throw Fail{MOSAIC_ERR_UNSUPPORTED, "colour schemes other than NONE are not implemented yet"};
 }
 
 void make_plans(G *g)
@@ -369,7 +367,22 @@ void run_pipeline(G *g, bool candidates_only)
     const bool is_lab = g->diff_type != MOSAIC_RGB_EUCLIDEAN;
     const bool with_chroma = g->diff_type == MOSAIC_CIEDE2000;
     const int kern_type = with_chroma ? MM_DIFF_CIEDE2000 : MM_DIFF_EUCLID;
-    const int V = 1;  // scheme NONE only for now (faithful quirk mode also compares a single variant)
+    // Colour-scheme variants (ColourScheme.cpp:36-177): original + hue rotations. Reference quirk Q1: getCellAt builds the
+    // V cell Mats over ONE shared buffer (PhotomosaicGeneratorBase.cpp:310-312), so every variant holds the LAST rotation
+    // and the original image is never compared. faithful mode reproduces that with a single variant.
+    static const float kRot[6][3] = {{0, 0, 0}, {180, 0, 0}, {120, 240, 0}, {150, 210, 0}, {90, 180, 270}, {30, 60, 90}};
+    static const int kNumRot[6] = {0, 1, 2, 2, 3, 3};
+    std::vector<float> rotations;  // rotation of each variant that is actually compared (0 = the image itself)
+    if (g->scheme == MOSAIC_SCHEME_NONE)
+        rotations = {0.0f};
+    else if (g->quirk_faithful)
+        rotations = {kRot[g->scheme][kNumRot[g->scheme] - 1]};
+    else {
+        rotations = {0.0f};
+        for (int i = 0; i < kNumRot[g->scheme]; ++i)
+            rotations.push_back(kRot[g->scheme][i]);
+    }
+    const int V = (int)rotations.size();
     g->V_eff = V;
     const int64_t N = g->n_lib;
     const int n_lib_tiles = (int)((N + MM_TNB - 1) / MM_TNB);
@@ -387,10 +400,20 @@ void run_pipeline(G *g, bool candidates_only)
     // ---- Preprocess: main image -> working space (PhotomosaicGeneratorBase.cpp:223-252)
     t_pre.start();
     DevBuf &d_main_f32 = g->ws.main_f32;
-    d_main_f32.alloc((size_t)g->img_rows * g->img_cols * 3 * sizeof(float), st);
-    CU(launch_to_working_space(g->d_main_u8.as<uint8_t>(), (size_t)g->img_cols * 3, g->img_rows, g->img_cols,
-                               d_main_f32.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
-    tm.kernel_launches++;
+    const size_t n_main_px = (size_t)g->img_rows * g->img_cols;
+    d_main_f32.alloc((size_t)V * n_main_px * 3 * sizeof(float), st);
+    for (int v = 0; v < V; ++v) {
+        const uint8_t *src = g->d_main_u8.as<uint8_t>();
+        if (rotations[v] != 0.0f) {
+            g->ws.main_var_u8.alloc(n_main_px * 3, st);
+            CU(launch_hue_rotate(src, g->ws.main_var_u8.as<uint8_t>(), g->img_rows, g->img_cols, rotations[v], st));
+            tm.kernel_launches++;
+            src = g->ws.main_var_u8.as<uint8_t>();
+        }
+        CU(launch_to_working_space(src, (size_t)g->img_cols * 3, g->img_rows, g->img_cols, d_main_f32.as<float>() + (size_t)v * n_main_px * 3,
+                                   is_lab, g->d_lut.as<int16_t>(), nullptr, st));
+        tm.kernel_launches++;
+    }
 
     // ---- Preprocess: library -> working space at the detail size of step 0 (:255-290)
     DevBuf &d_lib_work = g->ws.lib_work, &d_lib_small = g->ws.lib_small;

@@ -230,6 +230,22 @@ int mosaic_kernel_bgr_to_lab(int device, const uint8_t *bgr, int64_t n_pixels, f
     return MOSAIC_OK;
 }
 
+int mosaic_kernel_hue_rotate(int device, const uint8_t *bgr, int rows, int cols, float rotation_degrees, uint8_t *out)
+{
+    const int64_t n_pixels = (int64_t)rows * cols;
+    if (!bgr || !out || rows <= 0 || cols <= 0)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    Dev d_in, d_out;
+    KCHECK(d_in.alloc((size_t)n_pixels * 3));
+    KCHECK(d_out.alloc((size_t)n_pixels * 3));
+    KCHECK(cudaMemcpy(d_in.p, bgr, (size_t)n_pixels * 3, cudaMemcpyHostToDevice));
+    KCHECK(launch_hue_rotate(d_in.as<uint8_t>(), d_out.as<uint8_t>(), rows, cols, rotation_degrees, 0));
+    KCHECK(cudaMemcpy(out, d_out.p, (size_t)n_pixels * 3, cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
 int mosaic_kernel_resize_area_u8(int device, const uint8_t *src, int64_t n, int size, int k, uint8_t *dst)
 {
     if (!src || !dst || n <= 0 || size <= 0 || k < 1 || size % k != 0)

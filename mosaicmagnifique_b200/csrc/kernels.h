@@ -32,6 +32,8 @@ cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, f
 // u8 BGR -> working space f32 AoS [pixel][3]: Lab through the OpenCV-compatible LUT (is_lab) or a plain cast.
 cudaError_t launch_to_working_space(const uint8_t *bgr, size_t row_stride, int rows, int cols, float *out, bool is_lab,
                                     const int16_t *lab_lut, const int *c8, cudaStream_t stream);
+// hue-rotated 8U copy of an 8U BGR image (ColourScheme.cpp:36-177, OpenCV float HSV_FULL round trip)
+cudaError_t launch_hue_rotate(const uint8_t *in, uint8_t *out, int rows, int cols, float rot, cudaStream_t stream);
 // INTER_AREA for integer ratios, 8U 3-channel, batch of n square images (src size s -> dst size s / k)
 cudaError_t launch_area_u8(const uint8_t *src, uint8_t *dst, int64_t n, int src_size, int k, cudaStream_t stream);
 // INTER_AREA for integer ratios, f32 3-channel, batch of n square images

@@ -89,6 +89,74 @@ cudaError_t launch_to_working_space(const uint8_t *bgr, size_t row_stride, int r
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ colour-scheme variants (hue rotation)
+// ColourScheme::getColourScheme* (src/Photomosaic/ColourScheme.cpp:36-177): 8U BGR -> f32 -> cvtColor(BGR2HSV_FULL)
+// -> H = fmod(H + rot, 360) -> cvtColor(HSV2BGR_FULL) -> convertTo(8U). OpenCV's float HSV code contracts a few
+// operations into FMAs (probed against cv2 4.13, bit-exact with the forms below):
+//   H = fma(c1 - c2, 60/(diff + eps), offset), offset in {0 or 360, 120, 240};  tab2 = V * fma(-S, f, 1);  tab3 = V * fma(-S, 1 - f, 1)
+// OpenCV converts rows in blocks of 8 pixels (8-lane float SIMD); the < 8 pixels left at the end of a row go through its
+// scalar code, where a negative red-sector hue gets "+ 360" as a separate rounded addition (`scalar_tail`).
+__device__ __forceinline__ void hue_rotate_pixel(const uint8_t *in, uint8_t *out, float rot, bool scalar_tail)
+{
+    const float b = (float)in[0], g = (float)in[1], r = (float)in[2];
+    const float eps = 1.1920928955078125e-07f;  // FLT_EPSILON
+    const float v = fmaxf(fmaxf(r, g), b), vmin = fminf(fminf(r, g), b);
+    const float diff = __fsub_rn(v, vmin);
+    const float s = __fdiv_rn(diff, __fadd_rn(fabsf(v), eps));
+    const float d = __fdiv_rn(60.0f, __fadd_rn(diff, eps));
+    float h;
+    if (v == r) {
+        if (scalar_tail) {
+            h = __fmul_rn(__fsub_rn(g, b), d);
+            if (h < 0.0f)
+                h = __fadd_rn(h, 360.0f);
+        } else {
+            h = __fmaf_rn(__fsub_rn(g, b), d, g < b ? 360.0f : 0.0f);
+        }
+    }
+    else if (v == g)
+        h = __fmaf_rn(__fsub_rn(b, r), d, 120.0f);
+    else
+        h = __fmaf_rn(__fsub_rn(r, g), d, 240.0f);
+    h = fmodf(__fadd_rn(h, rot), 360.0f);  // ColourScheme.cpp:52 etc.
+    // HSV2BGR_FULL
+    const float hs = __fmul_rn(h, 6.0f / 360.0f);
+    const float pre = truncf(hs);
+    const float f = __fsub_rn(hs, pre);
+    float tab[4];
+    tab[0] = v;
+    tab[1] = __fmul_rn(v, __fsub_rn(1.0f, s));
+    tab[2] = __fmul_rn(v, __fmaf_rn(-s, f, 1.0f));
+    tab[3] = __fmul_rn(v, __fmaf_rn(-s, __fsub_rn(1.0f, f), 1.0f));
+    int sector = (int)__fsub_rn(pre, __fmul_rn(truncf(__fmul_rn(pre, 1.0f / 6.0f)), 6.0f));
+    sector = min(max(sector, 0), 5);
+    const int sd[6][3] = {{1, 3, 0}, {1, 0, 2}, {3, 0, 1}, {0, 2, 1}, {0, 1, 3}, {2, 1, 0}};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float t = tab[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k)
+            t = (sd[sector][c] == k) ? tab[k] : t;
+        out[c] = (uint8_t)min(max(__float2int_rn(t), 0), 255);  // convertTo(8U): saturate_cast(cvRound)
+    }
+}
+
+__global__ void hue_rotate_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, size_t n, float rot, int cols)
+{
+    const int tail_from = cols - cols % 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        hue_rotate_pixel(in + i * 3, out + i * 3, rot, (int)(i % cols) >= tail_from);
+}
+
+cudaError_t launch_hue_rotate(const uint8_t *in, uint8_t *out, int rows, int cols, float rot, cudaStream_t stream)
+{
+    const size_t n_pixels = (size_t)rows * cols;
+    if (n_pixels == 0)
+        return cudaSuccess;
+    hue_rotate_kernel<<<grid_for(n_pixels, 256), 256, 0, stream>>>(in, out, n_pixels, rot, cols);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ INTER_AREA, integer ratio
 
 __global__ void area_u8_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int64_t n, int S, int k)

@@ -33,16 +33,18 @@ def _to_product_shape(o_shape):
     return s
 
 
-def _run_case(oracle, main, lib, o_shape, diff, detail, steps, rr, ra, use_oracle_grid_state=True):
+def _run_case(oracle, main, lib, o_shape, diff, detail, steps, rr, ra, use_oracle_grid_state=True, scheme=0, faithful=True):
     from mosaicmagnifique_b200 import CellGroup, PhotomosaicGenerator
     og = _oracle_group(oracle, o_shape, detail, steps)
     states = oracle.grid_state(og, main)
-    want = oracle.generate(main, lib, og, states, diff, 0, rr, ra, want_D=True)
+    want = oracle.generate(main, lib, og, states, diff, scheme, rr, ra, want_D=True, shared_buffer_quirk=faithful)
 
     gen = PhotomosaicGenerator(0)
     gen.setMainImage(main)
     gen.setLibrary(lib)
     gen.setColourDifference(diff)
+    gen.setColourScheme(scheme)
+    gen.setVariantQuirk(faithful)
     cg = CellGroup()
     cg.setCellShape(_to_product_shape(o_shape))
     cg.setDetail(detail)
@@ -73,7 +75,10 @@ def _run_case(oracle, main, lib, o_shape, diff, detail, steps, rr, ra, use_oracl
         ties += t
     tm = gen.getTimings()
     assert tm["kernel_launches"] > 0
-    assert tm["pixel_diffs"] == sum(w.nominal for w in want)
+    # the oracle (like the reference) evaluates all V aliased variants in faithful mode; the engine evaluates the one
+    # distinct variant, so its count is the oracle's divided by V there
+    n_var = {0: 1, 1: 2, 2: 3, 3: 3, 4: 4, 5: 4}[scheme]
+    assert tm["pixel_diffs"] * (n_var if faithful else 1) == sum(w.nominal for w in want)
     gen.close()
     return total, ties
 
@@ -155,3 +160,18 @@ def test_fractional_detail(oracle, diff, cell, detail):
     OpenCV's fractional INTER_AREA on the 8U library and on the f32 cells, reproduced on the GPU."""
     main, lib = _inputs(81 + diff, 210, 290, 40, cell)
     _run_case(oracle, main, lib, oracle.CellShape.square(cell), diff, detail, 0, 2, 150)
+
+
+@pytest.mark.parametrize("scheme", [1, 2, 3, 4, 5])
+def test_colour_schemes_faithful(oracle, scheme):
+    """CONSISTENCY/COMPARE_*_COLOUR_SCHEME_* (tst_Generator.h:373-439, detail 50 as there). Faithful mode reproduces the
+    reference's aliasing quirk: every cell variant holds the LAST hue rotation."""
+    main, lib = _inputs(90 + scheme, 200, 260, 50, 32)
+    _run_case(oracle, main, lib, oracle.CellShape.square(32), 2, 50, 0, 2, 200, scheme=scheme, faithful=True)
+
+
+@pytest.mark.parametrize("scheme,diff", [(1, 0), (4, 2), (5, 1)])
+def test_colour_schemes_all_variants(oracle, scheme, diff):
+    """The intended behaviour (quirk off): a cell takes the minimum over the original and every rotated variant."""
+    main, lib = _inputs(95 + scheme, 200, 260, 50, 32)
+    _run_case(oracle, main, lib, oracle.CellShape.square(32), diff, 100, 0, 2, 200, scheme=scheme, faithful=False)

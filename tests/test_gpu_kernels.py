@@ -164,3 +164,18 @@ def test_microbench_runs(L):
     out = np.zeros(8, np.float64)
     assert L.mosaic_kernel_microbench(0, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 8) == 0
     assert out[0] > 1e12 and out[2] > 1e11 and out[4] >= 100
+
+
+@pytest.mark.parametrize("rot", [180.0, 120.0, 240.0, 150.0, 210.0, 90.0, 270.0, 30.0, 60.0])
+def test_hue_rotation_matches_opencv(L, rot):
+    """ColourScheme variants (ColourScheme.cpp:36-177) against the OpenCV calls the reference makes, bit exact."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(int(rot))
+    img = rng.integers(0, 256, (257, 263, 3), dtype=np.uint8)
+    img[0, :256] = np.arange(256, dtype=np.uint8)[:, None]  # greys: S = 0
+    hsv = cv2.cvtColor(img.astype(np.float32), cv2.COLOR_BGR2HSV_FULL)
+    hsv[..., 0] = np.fmod(hsv[..., 0] + np.float32(rot), np.float32(360.0))
+    want = np.clip(np.rint(cv2.cvtColor(hsv, cv2.COLOR_HSV2BGR_FULL)), 0, 255).astype(np.uint8)
+    out = np.empty_like(img)
+    assert L.mosaic_kernel_hue_rotate(0, img.ctypes.data, img.shape[0], img.shape[1], rot, out.ctypes.data) == 0
+    assert np.array_equal(out, want), int((out != want).sum())
