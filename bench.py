@@ -32,7 +32,7 @@ if ROOT not in sys.path:
 # algorithmic work per pixel-difference of the REFERENCE formula
 WORK = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1}, 1: {"flop": 9, "sfu": 1}}
 # what this engine's kernel executes per pixel-difference (colour_math.cuh; instruction counts from SASS / ncu)
-EXECUTED = {2: {"mufu": 11}, 0: {"mufu": 1}, 1: {"mufu": 1}}
+EXECUTED = {2: {"mufu": 10, "fp32_lane_ops": 85}, 0: {"mufu": 1, "fp32_lane_ops": 7}, 1: {"mufu": 1, "fp32_lane_ops": 7}}
 
 WORKLOADS = {
     # name: (H, W, n_lib, cell, detail, diff, range, addition, seed)
@@ -122,7 +122,7 @@ def cpu_sample(cfg, main, lib, seconds):
     masks4 = og.detail_cells[0].masks4()
     prep_s = time.perf_counter() - t0
     # calibrate on one grid row, then take as many rows as fit the time budget
-    rows_done, visited, nominal, elapsed = 0, 0, 0, 0.0
+    rows_done, visited, nominal, elapsed, cells_done = 0, 0, 0, 0.0, 0
     y = 0
     while y < state.shape[0] and (rows_done == 0 or elapsed < seconds):
         if (state[y] >= 0).any():
@@ -133,10 +133,11 @@ def cpu_sample(cfg, main, lib, seconds):
             visited += r.visited
             nominal += r.nominal
             rows_done += 1
+            cells_done += int((state[y] >= 0).sum())
         y += 1
     return {"seconds": elapsed, "prep_seconds": prep_s, "visited": visited, "nominal": nominal, "rows": rows_done, "n_lib": n_lib,
-            "sample": "first %d grid row(s) (%d cells) x first %d library images of the workload, early exit on"
-                      % (rows_done, int(nominal // max(1, n_lib * cfg["cell"] ** 2 * (cfg["detail"] / 100.0) ** 2)), n_lib)}
+            "sample": "first %d grid row(s) with valid cells (%d cells) x first %d library images of the workload, early exit on"
+                      % (rows_done, cells_done, n_lib)}
 
 
 def run_reference(args, cfg):
@@ -187,7 +188,7 @@ def main():
     import torch.distributed as dist
 
     from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator, capi, synthetic
-    from mosaicmagnifique_b200.parallel import generate_sharded
+    from mosaicmagnifique_b200.parallel import generate_sharded, set_library_sharded
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,9 +221,15 @@ def main():
     gen.setCellGroup(cg)
     gen.setRepeat(cfg["rr"], cfg["ra"])
 
+    h2d_lib = [lib_t.numel()]
+
     def load_inputs():
         gen.setMainImagePtr(main_t.data_ptr(), H, W, W * 3)
-        gen.setLibraryPtr(lib_t.data_ptr(), N, S)
+        if world > 1:
+            # replicated library: each rank uploads 1/world over PCIe, the rest arrives over NVLink (NCCL all-gather)
+            h2d_lib[0] = set_library_sharded(gen, lib_t, rank, world)
+        else:
+            gen.setLibraryPtr(lib_t.data_ptr(), N, S)
 
     load_inputs()
     state = gen.computeGridState()
@@ -281,7 +288,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_elapsed = t.item()
     e2e_value = pixel_diffs / (e2e_elapsed / e2e_steps)
-    h2d = int(main_t.numel() + lib_t.numel())
+    h2d = int(main_t.numel() + h2d_lib[0])  # per rank
     d2h = int(sum(g.size * 8 for g in grids))
 
     if rank != 0:
@@ -292,9 +299,9 @@ def main():
     # ---- roofline of the dominant kernel (diff_sum), live numbers
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
-    mb = np.zeros(8)
+    mb = np.zeros(12)
     import ctypes
-    capi().mosaic_kernel_microbench(local_rank, mb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 8)
+    capi().mosaic_kernel_microbench(local_rank, mb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 12)
     diff_s = phase["diff_ms"] * 1e-3 / args.steps                  # average duration of the one diff launch per step (CUDA events)
     units_per_launch = pixel_diffs * local_share                    # pixel-diffs the launch on this GPU processes
     work = WORK[cfg["diff"]]
@@ -308,11 +315,17 @@ def main():
         "traffic": None,
         "note": "SURVEY 8d counts the REFERENCE formula: %d flop + %d special-function ops per pixel-diff; peak = MUFU.RSQ rate "
                 "measured live by the in-library micro-benchmark (16 lanes/clk/SM). The kernel's trig-free CIEDE2000 executes only "
-                "%d MUFU ops per pixel-diff, which is why frac can exceed 1; see executed_*" % (work["flop"], work["sfu"], EXECUTED[cfg["diff"]]["mufu"]),
+                "%d MUFU ops and %d FP32 lane-ops per pixel-diff, which is why frac can exceed 1; see executed_* (pipe utilisation "
+                "of what actually runs) and mixed_pipe_ceiling (a synthetic loop with the kernel's instruction mix)"
+                % (work["flop"], work["sfu"], EXECUTED[cfg["diff"]]["mufu"], EXECUTED[cfg["diff"]]["fp32_lane_ops"]),
         "fp32": {"achieved_tflops": flop_rate / 1e12, "peak_tflops": 2 * mb[1] / 1e12, "frac": flop_rate / (2 * mb[1]),
                  "peak_source": "live FFMA2 micro-benchmark x 2 flop"},
         "executed_mufu": {"achieved_gops": EXECUTED[cfg["diff"]]["mufu"] * units_per_launch / diff_s / 1e9, "peak_gops": mb[2] / 1e9,
                           "frac": EXECUTED[cfg["diff"]]["mufu"] * units_per_launch / diff_s / mb[2]},
+        "executed_fp32": {"achieved_lane_ops_per_s": EXECUTED[cfg["diff"]]["fp32_lane_ops"] * units_per_launch / diff_s,
+                          "peak_lane_ops_per_s": mb[1], "frac": EXECUTED[cfg["diff"]]["fp32_lane_ops"] * units_per_launch / diff_s / mb[1],
+                          "peak_source": "live FFMA2 micro-benchmark (packed FP32 lane-ops/s)"},
+        "mixed_pipe_ceiling_pixel_diffs_per_s": mb[6] if cfg["diff"] == 2 else None,
         "hbm": {"min_bytes_per_launch": min_bytes, "achieved_gbs": min_bytes / diff_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                 "frac": (min_bytes / diff_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"},
@@ -329,7 +342,8 @@ def main():
                       "repeat": [cfg["rr"], cfg["ra"]], "pixel_diffs_per_step": pixel_diffs,
                       "cache": "inputs (%.1f GB packed library + cells per step) exceed the 126 MB L2; nothing is reused across steps"
                                % (min_bytes / 1e9),
-                      "parallelism": "grid rows sharded over %d GPU(s), library replicated, top-K candidates all-gathered (NCCL)" % world
+                      "parallelism": "valid cells (raster order) sharded over %d GPU(s), library replicated (e2e: uploaded in 1/N slices "
+                                     "and all-gathered over NVLink), top-K candidates all-gathered (NCCL)" % world
                       if world > 1 else "1 GPU"},
            "generate_ms": ms_per_step,
            "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
@@ -338,7 +352,7 @@ def main():
            "gpu_launches": int(launches),
            "clocks": clk, "roofline": roofline,
            "microbench": {"ffma_lane_ops_per_s": mb[0], "ffma2_lane_ops_per_s": mb[1], "mufu_rsq_per_s": mb[2], "mufu_ex2_per_s": mb[3],
-                          "sm_count": int(mb[4])}}
+                          "sm_count": int(mb[4]), "ciede_mix_pairs_per_s": mb[6]}}
 
     if not args.no_cpu_baseline and world == 1:
         cs = cpu_sample(cfg, main_np, lib_np, args.cpu_seconds)

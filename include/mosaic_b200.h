@@ -79,10 +79,10 @@ const char *mosaic_last_error(const mosaic_generator *g); /* replaces the modal 
 const char *mosaic_version(void);
 
 /* ---- setters: PhotomosaicGeneratorBase.h:40-66, .cpp:45-93 */
-/* setMainImage(const cv::Mat&): 8U BGR, rows x cols, row_stride in bytes (>= cols*3) */
+/* setMainImage(const cv::Mat&): 8U BGR, rows x cols, row_stride in bytes (>= cols*3). Host OR device pointer (unified addressing). */
 int mosaic_set_main_image(mosaic_generator *g, const uint8_t *bgr, int rows, int cols, size_t row_stride);
 /* setLibrary(const std::vector<cv::Mat>&): n square 8U BGR images of size x size, contiguous.
- * As in the reference the images must already be at the cell size (MainWindow.cpp:575-581). */
+ * As in the reference the images must already be at the cell size (MainWindow.cpp:575-581). Host OR device pointer. */
 int mosaic_set_library(mosaic_generator *g, const uint8_t *bgr, int64_t n, int size);
 int mosaic_set_colour_difference(mosaic_generator *g, int type); /* setColourDifference */
 int mosaic_set_colour_scheme(mosaic_generator *g, int type);     /* setColourScheme */

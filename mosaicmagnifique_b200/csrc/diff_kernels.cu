@@ -190,13 +190,10 @@ static cudaError_t launch(const void *cells, const void *lib, float *D, unsigned
                           int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream)
 {
     const size_t smem = (size_t)kStages * kStageBytes;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(diff_sum_kernel<DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return e;
-        configured = true;
-    }
+    // per device (context) attribute: set on every launch, it is cheap
+    cudaError_t e = cudaFuncSetAttribute(diff_sum_kernel<DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+        return e;
     dim3 grid(n_cell_tiles, n_lib_tiles);
     diff_sum_kernel<DIFF><<<grid, kThreads, smem, stream>>>((const unsigned char *)cells, (const unsigned char *)lib, D,
                                                              best_key, n_chunks, n_lib, n_lib_tiles * MM_TNB, n_cells);
@@ -210,9 +207,9 @@ cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, f
         return cudaSuccess;
     if (n_lib_tiles > 65535)
         return cudaErrorInvalidValue;
-    if (diff_type == MM_DIFF_CIEDE2000)
-        return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream);
-    return launch<MM_DIFF_EUCLID>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream);
+    if (diff_type != MM_DIFF_CIEDE2000)
+        return cudaErrorInvalidValue;  // RGB Euclidean / CIE76 run diff_euclid_kernel (diff_euclid.cu)
+    return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream);
 }
 
 }  // namespace mm

@@ -323,19 +323,14 @@ void make_plans(G *g)
                     p.next_x.push_back(gs.cols);
                 }
         }
-        // rank's block of cells: contiguous grid rows, balanced by valid-cell count
+        // rank's block of cells: a contiguous raster range of the step's valid cells (grid rows, cut at cell granularity
+        // on whole cell tiles so that every rank launches the same number of CTAs +- 1 tile)
         const int64_t n = (int64_t)p.cell_pos.size();
-        auto row_start_cell = [&](int64_t target) {
-            // first cell index >= target that starts a grid row
-            int64_t c = std::min(target, n);
-            while (c > 0 && c < n && p.cell_pos[c] / gs.cols == p.cell_pos[c - 1] / gs.cols)
-                ++c;
-            return c;
-        };
-        p.cell_begin = g->rank == 0 ? 0 : row_start_cell(n * g->rank / g->world);
-        p.cell_end = g->rank == g->world - 1 ? n : row_start_cell(n * (g->rank + 1) / g->world);
-        if (p.cell_end < p.cell_begin)
-            p.cell_end = p.cell_begin;
+        const int tcb = tile_geom(g->diff_type == MOSAIC_CIEDE2000 ? kLayoutCiede : kLayoutEuclid).tcb;
+        const int64_t n_tiles = (n + tcb - 1) / tcb;
+        auto cut = [&](int r) { return std::min<int64_t>(n, (n_tiles * r / g->world) * tcb); };
+        p.cell_begin = cut(g->rank);
+        p.cell_end = g->rank == g->world - 1 ? n : cut(g->rank + 1);
     }
 }
 
@@ -365,8 +360,8 @@ void run_pipeline(G *g, bool candidates_only)
     g->timings = mosaic_timings{};
     mosaic_timings &tm = g->timings;
     const bool is_lab = g->diff_type != MOSAIC_RGB_EUCLIDEAN;
-    const bool with_chroma = g->diff_type == MOSAIC_CIEDE2000;
-    const int kern_type = with_chroma ? MM_DIFF_CIEDE2000 : MM_DIFF_EUCLID;
+    const PackLayout layout = g->diff_type == MOSAIC_CIEDE2000 ? kLayoutCiede : kLayoutEuclid;
+    const TileGeom tg = tile_geom(layout);
     // Colour-scheme variants (ColourScheme.cpp:36-177): original + hue rotations. Reference quirk Q1: getCellAt builds the
     // V cell Mats over ONE shared buffer (PhotomosaicGeneratorBase.cpp:310-312), so every variant holds the LAST rotation
     // and the original image is never compared. faithful mode reproduces that with a single variant.
@@ -385,8 +380,8 @@ void run_pipeline(G *g, bool candidates_only)
     const int V = (int)rotations.size();
     g->V_eff = V;
     const int64_t N = g->n_lib;
-    const int n_lib_tiles = (int)((N + MM_TNB - 1) / MM_TNB);
-    const int n_lib_pad = n_lib_tiles * MM_TNB;
+    const int n_lib_tiles = (int)((N + tg.tnb - 1) / tg.tnb);
+    const int n_lib_pad = n_lib_tiles * tg.tnb;
     const size_t n_steps = g->grid.size();
     Timer t_pre(st), t_diff(st), t_sel(st);
     double pre_ms = 0, diff_ms = 0, sel_ms = 0;
@@ -483,7 +478,7 @@ void run_pipeline(G *g, bool candidates_only)
             if (m4[i] | m4[(size_t)P + i] | m4[(size_t)2 * P + i] | m4[(size_t)3 * P + i])
                 pix.push_back(i);
         p.n_active = (int)pix.size();
-        p.n_chunks = std::max(1, (p.n_active + MM_KP - 1) / MM_KP);
+        p.n_chunks = std::max(1, (p.n_active + tg.kp - 1) / tg.kp);
         d.pix_list.alloc(std::max<size_t>(pix.size(), 1) * sizeof(int), st);
         CU(cudaMemcpyAsync(d.pix_list.p, pix.data(), pix.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         d.masks4.alloc(m4.size(), st);
@@ -491,9 +486,9 @@ void run_pipeline(G *g, bool candidates_only)
         tm.h2d_bytes += (double)(pix.size() * sizeof(int) + m4.size());
 
         // library tiles
-        d.lib_packed.alloc((size_t)n_lib_tiles * p.n_chunks * (MM_TNB * MM_KP * 16), st);
+        d.lib_packed.alloc((size_t)n_lib_tiles * p.n_chunks * tg.lib_block, st);
         CU(launch_pack_library(d_lib_work.as<float>(), d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
-                               n_lib_tiles, with_chroma, st));
+                               n_lib_tiles, layout, st));
         tm.kernel_launches++;
 
         // cell descriptors of this rank's cells (getCellAt, PhotomosaicGeneratorBase.cpp:293-329)
@@ -526,18 +521,18 @@ void run_pipeline(G *g, bool candidates_only)
         tm.pixel_diffs_nominal += p.pixel_diffs_nominal;
 
         const int n_rows_local = (int)(n_local * V);
-        const int n_cell_tiles = (n_rows_local + MM_TCB - 1) / MM_TCB;
-        const int n_rows_pad = n_cell_tiles * MM_TCB;
+        const int n_cell_tiles = (n_rows_local + tg.tcb - 1) / tg.tcb;
+        const int n_rows_pad = n_cell_tiles * tg.tcb;
         d.descs.alloc(std::max<size_t>(descs.size(), 1) * sizeof(CellDesc), st);
         CU(cudaMemcpyAsync(d.descs.p, descs.data(), descs.size() * sizeof(CellDesc), cudaMemcpyHostToDevice, st));
         tm.h2d_bytes += (double)(descs.size() * sizeof(CellDesc));
-        d.cells_packed.alloc((size_t)std::max(n_cell_tiles, 1) * p.n_chunks * (MM_TCB * MM_KP * 20), st);
+        d.cells_packed.alloc((size_t)std::max(n_cell_tiles, 1) * p.n_chunks * tg.cell_block, st);
         AreaTab cell_tab{nullptr, nullptr, nullptr};
         if (p.k == 0)
             cell_tab = upload_area_table(g, p.S, p.ds, tm);
         CU(launch_extract_cells(d_main_f32.as<float>(), g->img_rows, g->img_cols, d.descs.as<CellDesc>(), n_rows_local, p.S, p.ds,
                                 p.k, cell_tab, d.masks4.as<uint8_t>(), d.pix_list.as<int>(), p.n_active, p.n_chunks,
-                                d.cells_packed.p, with_chroma, st));
+                                d.cells_packed.p, layout, st));
         tm.kernel_launches++;
         t_pre.stop();
         pre_ms += t_pre.ms();
@@ -556,9 +551,14 @@ void run_pipeline(G *g, bool candidates_only)
             CU(launch_fill_u64(d.best_key.as<unsigned long long>(), (size_t)std::max(n_rows_pad, 1), ~0ull, st));
             tm.kernel_launches++;
         }
-        CU(launch_diff_sum(kern_type, d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
-                           fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
-                           (int)N, n_rows_local, st));
+        if (layout == kLayoutCiede)
+            CU(launch_diff_sum(MM_DIFF_CIEDE2000, d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
+                               fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
+                               (int)N, n_rows_local, st));
+        else
+            CU(launch_diff_euclid(d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
+                                  fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
+                                  (int)N, n_rows_local, st));
         if (n_cell_tiles > 0)
             tm.kernel_launches++;
         t_diff.stop();
@@ -698,12 +698,12 @@ int mosaic_set_main_image(mosaic_generator *g, const uint8_t *bgr, int rows, int
         if (!a.bgr || a.rows <= 0 || a.cols <= 0 || a.stride < (size_t)a.cols * 3)
             throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "main image must be a non-empty 8U BGR image"};
         g->d_main_u8.alloc((size_t)a.rows * a.cols * 3, g->stream);
-        CU(cudaMemcpy2DAsync(g->d_main_u8.p, (size_t)a.cols * 3, a.bgr, a.stride, (size_t)a.cols * 3, a.rows, cudaMemcpyHostToDevice,
+        // host or device pointer (unified addressing): cudaMemcpyDefault lets the driver pick the direction
+        CU(cudaMemcpy2DAsync(g->d_main_u8.p, (size_t)a.cols * 3, a.bgr, a.stride, (size_t)a.cols * 3, a.rows, cudaMemcpyDefault,
                              g->stream));
-        g->h_main.resize((size_t)a.rows * a.cols * 3);
-        for (int y = 0; y < a.rows; ++y)
-            memcpy(&g->h_main[(size_t)y * a.cols * 3], a.bgr + (size_t)y * a.stride, (size_t)a.cols * 3);
         CU(cudaStreamSynchronize(g->stream));
+        // host copy for getGridState's entropy rule; fetched lazily from the device when it is needed
+        g->h_main.clear();
         g->img_rows = a.rows;
         g->img_cols = a.cols;
     }, &a);
@@ -723,7 +723,7 @@ int mosaic_set_library(mosaic_generator *g, const uint8_t *bgr, int64_t n, int s
         if (a.n * a.size > INT32_MAX)
             throw Fail{MOSAIC_ERR_UNSUPPORTED, "library too large (n * size must fit 31 bits)"};
         g->d_lib_u8.alloc((size_t)a.n * a.size * a.size * 3, g->stream);
-        CU(cudaMemcpyAsync(g->d_lib_u8.p, a.bgr, g->d_lib_u8.bytes, cudaMemcpyHostToDevice, g->stream));
+        CU(cudaMemcpyAsync(g->d_lib_u8.p, a.bgr, g->d_lib_u8.bytes, cudaMemcpyDefault, g->stream));  // host or device pointer
         CU(cudaStreamSynchronize(g->stream));
         g->n_lib = a.n;
         g->lib_size = a.size;
@@ -826,7 +826,16 @@ int mosaic_compute_grid_state(mosaic_generator *g)
     if (!g->have_group || g->img_rows == 0)
         return g->fail(MOSAIC_ERR_NOT_READY, "getGridState: main image and cell group must be set");
     std::string err;
-    if (!compute_grid_state(g->group, g->h_main.data(), g->img_rows, g->img_cols, (size_t)g->img_cols * 3, g->grid, err))
+    if (g->h_main.empty() && g->group.size_steps > 0) {  // only the entropy rule of multi-step groups reads pixels
+        g->h_main.resize((size_t)g->img_rows * g->img_cols * 3);
+        cudaSetDevice(g->device);
+        if (cudaMemcpy(g->h_main.data(), g->d_main_u8.p, g->h_main.size(), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            return g->fail(MOSAIC_ERR_CUDA, "getGridState: reading the main image back failed");
+        }
+    }
+    if (!compute_grid_state(g->group, g->group.size_steps > 0 ? g->h_main.data() : nullptr, g->img_rows, g->img_cols,
+                            (size_t)g->img_cols * 3, g->grid, err))
         return g->fail(MOSAIC_ERR_UNSUPPORTED, "getGridState: " + err);
     return MOSAIC_OK;
 }
@@ -926,7 +935,8 @@ int mosaic_get_differences(const mosaic_generator *g, int step, float *out, int6
         return MOSAIC_ERR_INVALID_ARGUMENT;
     if (n_local == 0)
         return MOSAIC_OK;
-    const int n_lib_pad = (int)((g->n_lib + MM_TNB - 1) / MM_TNB) * MM_TNB;
+    const int tnb = tile_geom(g->diff_type == MOSAIC_CIEDE2000 ? kLayoutCiede : kLayoutEuclid).tnb;
+    const int n_lib_pad = (int)((g->n_lib + tnb - 1) / tnb) * tnb;
     cudaSetDevice(g->device);
     cudaError_t e = cudaMemcpy2D(out, (size_t)n_lib * sizeof(float), g->d_D[step].p, (size_t)g->V_eff * n_lib_pad * sizeof(float),
                                  (size_t)n_lib * sizeof(float), (size_t)n_local, cudaMemcpyDeviceToHost);

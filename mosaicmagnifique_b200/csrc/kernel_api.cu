@@ -61,10 +61,12 @@ int difference_sums(int type, const float *cells, int n_cells, const float *lib,
         if (mask[i])
             pix.push_back(i);
     const int n_active = (int)pix.size();
-    const int n_chunks = std::max(1, (n_active + MM_KP - 1) / MM_KP);
-    const int n_lib_tiles = (int)((n_lib + MM_TNB - 1) / MM_TNB), n_lib_pad = n_lib_tiles * MM_TNB;
-    const int n_cell_tiles = (n_cells + MM_TCB - 1) / MM_TCB, n_cells_pad = n_cell_tiles * MM_TCB;
     const bool chroma = type == MOSAIC_CIEDE2000;
+    const PackLayout layout = chroma ? kLayoutCiede : kLayoutEuclid;
+    const TileGeom tg = tile_geom(layout);
+    const int n_chunks = std::max(1, (n_active + tg.kp - 1) / tg.kp);
+    const int n_lib_tiles = (int)((n_lib + tg.tnb - 1) / tg.tnb), n_lib_pad = n_lib_tiles * tg.tnb;
+    const int n_cell_tiles = (n_cells + tg.tcb - 1) / tg.tcb, n_cells_pad = n_cell_tiles * tg.tcb;
     std::vector<uint8_t> m4((size_t)4 * P, 0);
     for (int i = 0; i < P; ++i)
         m4[i] = mask[i] ? 255 : 0;
@@ -85,24 +87,27 @@ int difference_sums(int type, const float *cells, int n_cells, const float *lib,
     KCHECK(d_pix.alloc(pix.size() * sizeof(int)));
     KCHECK(d_m4.alloc(m4.size()));
     KCHECK(d_desc.alloc(descs.size() * sizeof(CellDesc)));
-    KCHECK(d_cp.alloc((size_t)n_cell_tiles * n_chunks * (MM_TCB * MM_KP * 20)));
-    KCHECK(d_lp.alloc((size_t)n_lib_tiles * n_chunks * (MM_TNB * MM_KP * 16)));
+    KCHECK(d_cp.alloc((size_t)n_cell_tiles * n_chunks * tg.cell_block));
+    KCHECK(d_lp.alloc((size_t)n_lib_tiles * n_chunks * tg.lib_block));
     KCHECK(d_D.alloc((size_t)n_cells_pad * n_lib_pad * sizeof(float)));
     KCHECK(cudaMemcpy(d_cells.p, cells, (size_t)n_cells * P * 3 * sizeof(float), cudaMemcpyHostToDevice));
     KCHECK(cudaMemcpy(d_lib.p, lib, (size_t)n_lib * P * 3 * sizeof(float), cudaMemcpyHostToDevice));
     KCHECK(cudaMemcpy(d_pix.p, pix.data(), pix.size() * sizeof(int), cudaMemcpyHostToDevice));
     KCHECK(cudaMemcpy(d_m4.p, m4.data(), m4.size(), cudaMemcpyHostToDevice));
     KCHECK(cudaMemcpy(d_desc.p, descs.data(), descs.size() * sizeof(CellDesc), cudaMemcpyHostToDevice));
-    KCHECK(launch_pack_library(d_lib.as<float>(), d_lp.p, n_lib, P, d_pix.as<int>(), n_active, n_chunks, n_lib_tiles, chroma, 0));
+    KCHECK(launch_pack_library(d_lib.as<float>(), d_lp.p, n_lib, P, d_pix.as<int>(), n_active, n_chunks, n_lib_tiles, layout, 0));
     // the cells stacked vertically form one "main image" of n_cells*size rows; cell c sits at y0 = c*size; the bound
     // is relative to the cell, so descs carry by/bx in cell space (extract_cells tests bounds in detail space, k = 1)
     for (int c = 0; c < n_cells; ++c)
         descs[c].y0 = c * size;
     KCHECK(launch_extract_cells(d_cells.as<float>(), n_cells * size, size, d_desc.as<CellDesc>(), n_cells, size, size, 1,
                                 AreaTab{nullptr, nullptr, nullptr}, d_m4.as<uint8_t>(), d_pix.as<int>(), n_active, n_chunks, d_cp.p,
-                                chroma, 0));
-    KCHECK(launch_diff_sum(chroma ? MM_DIFF_CIEDE2000 : MM_DIFF_EUCLID, d_cp.p, d_lp.p, d_D.as<float>(), nullptr, n_cell_tiles,
-                           n_lib_tiles, n_chunks, (int)n_lib, n_cells, 0));
+                                layout, 0));
+    if (chroma)
+        KCHECK(launch_diff_sum(MM_DIFF_CIEDE2000, d_cp.p, d_lp.p, d_D.as<float>(), nullptr, n_cell_tiles, n_lib_tiles, n_chunks, (int)n_lib,
+                               n_cells, 0));
+    else
+        KCHECK(launch_diff_euclid(d_cp.p, d_lp.p, d_D.as<float>(), nullptr, n_cell_tiles, n_lib_tiles, n_chunks, (int)n_lib, n_cells, 0));
     KCHECK(cudaMemcpy2D(out, (size_t)n_lib * sizeof(float), d_D.p, (size_t)n_lib_pad * sizeof(float), (size_t)n_lib * sizeof(float),
                         n_cells, cudaMemcpyDeviceToHost));
     return MOSAIC_OK;

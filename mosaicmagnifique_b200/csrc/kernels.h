@@ -22,7 +22,28 @@
 #define MM_MIN_CTAS 2  // __launch_bounds__ residency target of the difference kernel
 #endif
 
+// tile geometry of the Euclidean / CIE76 kernel (see diff_euclid.cu)
+#define MM_ETC 64   // cells per cell tile
+#define MM_ETN 64   // library images per library tile
+#define MM_EKP 16   // pixels per chunk
+
 namespace mm {
+
+// which packed layout the prep kernels produce
+enum PackLayout { kLayoutCiede = 0, kLayoutEuclid = 1 };
+struct TileGeom {
+    int tcb, tnb, kp;
+    size_t cell_block, lib_block;  // bytes of one (tile, chunk) block
+};
+inline TileGeom tile_geom(PackLayout l)
+{
+    return l == kLayoutEuclid ? TileGeom{MM_ETC, MM_ETN, MM_EKP, (size_t)MM_EKP * 4 * MM_ETC * 4, (size_t)MM_EKP * 3 * MM_ETN * 4}
+                              : TileGeom{MM_TCB, MM_TNB, MM_KP, (size_t)MM_TCB * MM_KP * 20, (size_t)MM_TNB * MM_KP * 16};
+}
+
+// ---- diff_euclid.cu
+cudaError_t launch_diff_euclid(const void *cells, const void *lib, float *D, unsigned long long *best_key, int n_cell_tiles,
+                               int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream);
 
 // ---- diff_kernels.cu
 cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, float *D, unsigned long long *best_key,
@@ -50,7 +71,7 @@ cudaError_t launch_area_general_f32(const float *src, float *dst, int64_t n, int
                                     cudaStream_t stream);
 // working f32 AoS library [n][P][3] -> packed float4 tiles (compacted pixel order, chroma in .w)
 cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
-                                int n_chunks, int n_lib_tiles, bool with_chroma, cudaStream_t stream);
+                                int n_chunks, int n_lib_tiles, PackLayout layout, cudaStream_t stream);
 
 struct CellDesc {
     int x0, y0;          // top-left of the (unclipped) cell rect in main-image space
@@ -62,7 +83,7 @@ struct CellDesc {
 // k > 0: integer ratio S / ds = k; k == 0: fractional ratio through `tab` (detail size ds)
 cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int ds, int k,
                                  AreaTab tab, const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks,
-                                 void *packed, bool with_chroma, cudaStream_t stream);
+                                 void *packed, PackLayout layout, cudaStream_t stream);
 
 // ---- select_kernels.cu
 cudaError_t launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t stream);

@@ -320,8 +320,9 @@ __device__ __forceinline__ float4 half_scale_lab(float L, float a, float b)
 }
 
 __global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
-                                    const int *__restrict__ pix_list, int n_active, int n_chunks, bool with_chroma)
+                                    const int *__restrict__ pix_list, int n_active, int n_chunks, int layout)
 {
+    const bool with_chroma = layout == kLayoutCiede;
     // one thread per (image, active pixel)
     const size_t total = (size_t)n * n_active;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -331,6 +332,16 @@ __global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char
         float4 v = make_float4(s[0], s[1], s[2], 0.0f);
         if (with_chroma)
             v = half_scale_lab(v.x, v.y, v.z);
+        if (layout == kLayoutEuclid) {
+            // pixel-major, NEGATED: [lib_tile][chunk][pixel][x0,x1,x2][64 images] (diff_euclid.cu)
+            const size_t tile = im / MM_ETN, ti = im % MM_ETN;
+            const int chunk = q / MM_EKP, pi = q % MM_EKP;
+            float *f = reinterpret_cast<float *>(packed + (tile * n_chunks + chunk) * (size_t)(MM_EKP * 3 * MM_ETN * 4));
+            f[(pi * 3 + 0) * MM_ETN + ti] = -v.x;
+            f[(pi * 3 + 1) * MM_ETN + ti] = -v.y;
+            f[(pi * 3 + 2) * MM_ETN + ti] = -v.z;
+            continue;
+        }
         const size_t tile = im / MM_TNB, ti = im % MM_TNB;
         const int chunk = q / MM_KP, pi = q % MM_KP;
         unsigned char *blk = packed + (tile * n_chunks + chunk) * (size_t)(MM_TNB * MM_KP * 16);
@@ -348,24 +359,25 @@ __global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char
 }
 
 cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
-                                int n_chunks, int n_lib_tiles, bool with_chroma, cudaStream_t stream)
+                                int n_chunks, int n_lib_tiles, PackLayout layout, cudaStream_t stream)
 {
-    cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_lib_tiles * n_chunks * (MM_TNB * MM_KP * 16), stream);
+    cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_lib_tiles * n_chunks * tile_geom(layout).lib_block, stream);
     if (e != cudaSuccess)
         return e;
     const size_t total = (size_t)n * n_active;
     if (total == 0)
         return cudaSuccess;
     pack_library_kernel<<<grid_for(total, 256), 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active,
-                                                                  n_chunks, with_chroma);
+                                                                  n_chunks, (int)layout);
     return cudaGetLastError();
 }
 
 __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int W, const CellDesc *__restrict__ cells,
                                      int n_cells, int S, int ds, int k, AreaTab tab, const uint8_t *__restrict__ masks4,
                                      const int *__restrict__ pix_list, int n_active, int n_chunks,
-                                     unsigned char *__restrict__ packed, bool with_chroma)
+                                     unsigned char *__restrict__ packed, int layout)
 {
+    const bool with_chroma = layout == kLayoutCiede;
     const size_t total = (size_t)n_cells * n_active;
     const size_t block_bytes = (size_t)MM_TCB * MM_KP * 20;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -391,6 +403,17 @@ __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int
         }
         const bool in_bound = px >= cd.bx && px < cd.bx + cd.bw && py >= cd.by && py < cd.by + cd.bh;
         const bool active = masks4[((size_t)cd.flip * ds + py) * ds + px] != 0;
+        if (layout == kLayoutEuclid) {
+            // pixel-major: [cell_tile][chunk][pixel][x0,x1,x2,w][64 cells] (diff_euclid.cu)
+            const size_t tile = c / MM_ETC, ti = c % MM_ETC;
+            const int chunk = q / MM_EKP, pi = q % MM_EKP;
+            float *f = reinterpret_cast<float *>(packed + (tile * n_chunks + chunk) * (size_t)(MM_EKP * 4 * MM_ETC * 4));
+            f[(pi * 4 + 0) * MM_ETC + ti] = v[0];
+            f[(pi * 4 + 1) * MM_ETC + ti] = v[1];
+            f[(pi * 4 + 2) * MM_ETC + ti] = v[2];
+            f[(pi * 4 + 3) * MM_ETC + ti] = (in_bound && active) ? 1.0f : 0.0f;
+            continue;
+        }
         const size_t tile = c / MM_TCB, ti = c % MM_TCB;
         const int chunk = q / MM_KP, pi = q % MM_KP;
         unsigned char *blk = packed + (tile * n_chunks + chunk) * block_bytes;
@@ -404,17 +427,18 @@ __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int
 
 cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDesc *cells, int n_cells, int S, int ds, int k,
                                  AreaTab tab, const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks,
-                                 void *packed, bool with_chroma, cudaStream_t stream)
+                                 void *packed, PackLayout layout, cudaStream_t stream)
 {
-    const int n_tiles = (n_cells + MM_TCB - 1) / MM_TCB;
-    cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_tiles * n_chunks * (MM_TCB * MM_KP * 20), stream);
+    const TileGeom tg = tile_geom(layout);
+    const int n_tiles = (n_cells + tg.tcb - 1) / tg.tcb;
+    cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_tiles * n_chunks * tg.cell_block, stream);
     if (e != cudaSuccess)
         return e;
     const size_t total = (size_t)n_cells * n_active;
     if (total == 0)
         return cudaSuccess;
     extract_cells_kernel<<<grid_for(total, 256), 256, 0, stream>>>(mains, H, W, cells, n_cells, S, ds, k, tab, masks4, pix_list,
-                                                                   n_active, n_chunks, (unsigned char *)packed, with_chroma);
+                                                                   n_active, n_chunks, (unsigned char *)packed, (int)layout);
     return cudaGetLastError();
 }
 

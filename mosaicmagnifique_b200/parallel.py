@@ -53,6 +53,24 @@ def gather_rows(local: torch.Tensor, first: int, n_total: int, group=None) -> to
     return out
 
 
+def set_library_sharded(gen, lib_host: torch.Tensor, rank: int, world: int, group=None) -> int:
+    """setLibrary() for a replicated library without N full PCIe uploads: rank r copies only its 1/world slice of the
+    (pinned) host library to its GPU, the slices are all-gathered over NVLink, and the generator takes the device buffer
+    (mosaic_set_library accepts device pointers). Returns the bytes this rank moved host->device."""
+    n, size = lib_host.shape[0], lib_host.shape[1]
+    device = torch.device("cuda", gen.device)
+    per = -(-n // world)
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    row = size * size * 3
+    part = torch.zeros((per, row), dtype=torch.uint8, device=device)
+    part[:hi - lo].copy_(lib_host[lo:hi].reshape(hi - lo, row), non_blocking=True)
+    full = torch.empty((world * per, row), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(full, part, group=group)
+    torch.cuda.current_stream(device).synchronize()
+    gen.setLibraryPtr(full.data_ptr(), n, size)  # copies (device to device) before `full` is released
+    return (hi - lo) * row
+
+
 def generate_sharded(gen, rank: int, world: int, group=None):
     """generateBestFits() across `world` GPUs. Every rank holds the same inputs in its own generator; returns the
     best-fit grids (identical on every rank). bytes_exchanged is the all-gather payload this rank received."""
