@@ -165,6 +165,12 @@ int mosaic_kernel_microbench(int device, double *out, int n_out);
 void mosaic_grid_size(const mosaic_cell_shape *shape, int image_w, int image_h, int pad, int *grid_w, int *grid_h);
 void mosaic_rect_at(const mosaic_cell_shape *shape, int x, int y, int rect_xywh[4]);
 int mosaic_flip_at(const mosaic_cell_shape *shape, int x, int y); /* flip_h + 2 * flip_v */
+/* GridGenerator::getGridState (Grid/GridGenerator.cpp:29-193) with the reference's HOST arithmetic (the generator object
+ * evaluates the same rule on the GPU, mosaic_compute_grid_state). Steps are written back to back into out:
+ * step s holds step_rows[s] x step_cols[s] values, -1 = nullopt, 0 = valid. bgr may be NULL (no entropy rule). */
+int mosaic_host_grid_state(const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size, int detail_percent, int size_steps,
+                           const uint8_t *bgr, int rows, int cols, size_t row_stride, int max_steps, int *n_steps, int *step_rows,
+                           int *step_cols, int64_t *out, size_t out_capacity);
 /* cv::resize(INTER_AREA) for 8U images with cn channels (OpenCV-compatible, any down-scaling ratio) */
 int mosaic_host_resize_area_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w);
 

@@ -90,6 +90,7 @@ def capi():
         "mosaic_grid_size": (None, [shp, i, i, i, ip, ip]),
         "mosaic_rect_at": (None, [shp, i, i, ip]),
         "mosaic_flip_at": (i, [shp, i, i]),
+        "mosaic_host_grid_state": (i, [shp, vp, i, i, i, vp, i, i, sz, i, ip, ip, ip, vp, sz]),
         "mosaic_host_resize_area_u8": (i, [vp, i, i, i, vp, i, i]),
     }
     for name, (res, args) in sig.items():

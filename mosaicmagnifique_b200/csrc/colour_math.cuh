@@ -93,6 +93,18 @@ MM_HD float v_copysign(float a, float s) { return copysignf(a, s); }
 MM_HD float v_min(float a, float b) { return fminf(a, b); }
 MM_HD float v_max(float a, float b) { return fmaxf(a, b); }
 
+// a*b + c*d with each product rounded on its own. ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (even with
+// --fmad=false), so the packed version falls back to scalar __fmul_rn / __fadd_rn, which are never fused.
+#if defined(__CUDA_ARCH__)
+MM_HD float v_sum_of_products_unfused(float a, float b, float c, float d) { return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+#else
+MM_HD float v_sum_of_products_unfused(float a, float b, float c, float d)
+{
+    volatile float p = a * b, q = c * d;  // volatile: no contraction on the host either
+    return p + q;
+}
+#endif
+
 // ---- packed lane ops
 #if defined(__CUDA_ARCH__)
 MM_HD mm_f2 v_add(mm_f2 a, mm_f2 b) { const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)); return mm_f2{r.x, r.y}; }
@@ -107,6 +119,10 @@ MM_HD mm_f2 v_add(mm_f2 a, mm_f2 b) { return mm_f2{a.x + b.x, a.y + b.y}; }
 MM_HD mm_f2 v_mul(mm_f2 a, mm_f2 b) { return mm_f2{a.x * b.x, a.y * b.y}; }
 MM_HD mm_f2 v_fma(mm_f2 a, mm_f2 b, mm_f2 c) { return mm_f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
 #endif
+MM_HD mm_f2 v_sum_of_products_unfused(mm_f2 a, mm_f2 b, mm_f2 c, mm_f2 d)
+{
+    return mm_f2{v_sum_of_products_unfused(a.x, b.x, c.x, d.x), v_sum_of_products_unfused(a.y, b.y, c.y, d.y)};
+}
 MM_HD mm_f2 v_rsq(mm_f2 a) { return mm_f2{mm_rsq(a.x), mm_rsq(a.y)}; }
 MM_HD mm_f2 v_rcp(mm_f2 a) { return mm_f2{mm_rcp(a.x), mm_rcp(a.y)}; }
 MM_HD mm_f2 v_sqrt(mm_f2 a) { return mm_f2{mm_sqrt(a.x), mm_sqrt(a.y)}; }
@@ -166,7 +182,8 @@ MM_HD V mm_ciede2000_half_v(float L1, float a1, float b1, float C1, V L2, V a2, 
     // ---- dH' (:90-102) from dot / cross; dHq * sqrt2 = dH'/2
     const V P = v_fma(c1p, c2p, K(tiny));
     const V dot = v_fma(a1p, a2p, v_mul(K(b1), b2));
-    const V cross = v_fma(a1p, b2, v_mul(a2p, K(-b1)));
+    // two separately rounded products, never an FMA: identical colours must give cross == 0 and therefore dE == 0
+    const V cross = v_sum_of_products_unfused(a1p, b2, a2p, K(-b1));
     const auto pos = v_gt0(dot);
     const V argA = v_add(P, dot);
     const V argB = v_fma(dot, K(-1.0f), P);

@@ -124,7 +124,6 @@ struct mosaic_generator {
     // inputs
     int img_rows = 0, img_cols = 0;
     DevBuf d_main_u8;
-    std::vector<uint8_t> h_main;  // kept for compute_grid_state (host entropy rule)
     int64_t n_lib = 0;
     int lib_size = 0;
     DevBuf d_lib_u8;
@@ -702,8 +701,7 @@ int mosaic_set_main_image(mosaic_generator *g, const uint8_t *bgr, int rows, int
         CU(cudaMemcpy2DAsync(g->d_main_u8.p, (size_t)a.cols * 3, a.bgr, a.stride, (size_t)a.cols * 3, a.rows, cudaMemcpyDefault,
                              g->stream));
         CU(cudaStreamSynchronize(g->stream));
-        // host copy for getGridState's entropy rule; fetched lazily from the device when it is needed
-        g->h_main.clear();
+
         g->img_rows = a.rows;
         g->img_cols = a.cols;
     }, &a);
@@ -826,16 +824,37 @@ int mosaic_compute_grid_state(mosaic_generator *g)
     if (!g->have_group || g->img_rows == 0)
         return g->fail(MOSAIC_ERR_NOT_READY, "getGridState: main image and cell group must be set");
     std::string err;
-    if (g->h_main.empty() && g->group.size_steps > 0) {  // only the entropy rule of multi-step groups reads pixels
-        g->h_main.resize((size_t)g->img_rows * g->img_cols * 3);
-        cudaSetDevice(g->device);
-        if (cudaMemcpy(g->h_main.data(), g->d_main_u8.p, g->h_main.size(), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    // GridGenerator::getGridState with the entropy rule evaluated on the GPU (grid_kernels.cu), one batch per size step
+    EntropyEvaluator gpu_eval = [g](int step, const std::vector<EntropyCandidate> &cand, std::vector<uint8_t> &split,
+                                    std::string &e) -> bool {
+        try {
+            if (cudaSetDevice(g->device) != cudaSuccess)
+                throw Fail{MOSAIC_ERR_CUDA, "cudaSetDevice failed"};
+            cudaStream_t st = g->stream;
+            const Shape &dshape = g->group.detail_cells[step];
+            const std::vector<uint8_t> m4 = dshape.masks4();
+            std::vector<GridCandidate> gc(cand.size());
+            for (size_t i = 0; i < cand.size(); ++i)
+                gc[i] = GridCandidate{cand[i].cg.x, cand[i].cg.y, cand[i].cg.w, cand[i].cg.h, cand[i].db.x, cand[i].db.y,
+                                      cand[i].db.w, cand[i].db.h, cand[i].flip};
+            Workspace &w = g->ws;
+            w.masks4.alloc(m4.size(), st);
+            w.descs.alloc(gc.size() * sizeof(GridCandidate), st);
+            w.prog.alloc(gc.size(), st);
+            CU(cudaMemcpyAsync(w.masks4.p, m4.data(), m4.size(), cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(w.descs.p, gc.data(), gc.size() * sizeof(GridCandidate), cudaMemcpyHostToDevice, st));
+            CU(launch_grid_entropy(g->d_main_u8.as<uint8_t>(), g->img_cols, w.descs.as<GridCandidate>(), (int)gc.size(),
+                                   w.masks4.as<uint8_t>(), dshape.size, 8.0 * 0.7, w.prog.as<uint8_t>(), st));
+            CU(cudaMemcpyAsync(split.data(), w.prog.p, gc.size(), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            return true;
+        } catch (const Fail &f) {
             cudaGetLastError();
-            return g->fail(MOSAIC_ERR_CUDA, "getGridState: reading the main image back failed");
+            e = f.msg;
+            return false;
         }
-    }
-    if (!compute_grid_state(g->group, g->group.size_steps > 0 ? g->h_main.data() : nullptr, g->img_rows, g->img_cols,
-                            (size_t)g->img_cols * 3, g->grid, err))
+    };
+    if (!compute_grid_state(g->group, g->img_rows, g->img_cols, gpu_eval, g->grid, err))
         return g->fail(MOSAIC_ERR_UNSUPPORTED, "getGridState: " + err);
     return MOSAIC_OK;
 }
@@ -1057,6 +1076,47 @@ void mosaic_rect_at(const mosaic_cell_shape *shape, int x, int y, int rect_xywh[
 }
 
 int mosaic_flip_at(const mosaic_cell_shape *shape, int x, int y) { return flip_at(shape_params_only(*shape), x, y); }
+
+int mosaic_host_grid_state(const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size, int detail_percent, int size_steps,
+                           const uint8_t *bgr, int rows, int cols, size_t row_stride, int max_steps, int *n_steps, int *step_rows,
+                           int *step_cols, int64_t *out, size_t out_capacity)
+{
+    if (!shape || !mask || !n_steps || !step_rows || !step_cols || !out || rows <= 0 || cols <= 0)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    try {
+        Shape top;
+        shape_from_c(*shape, mask, top);
+        std::string err;
+        if (cell_size > 0 && cell_size != top.size) {
+            Shape r;
+            if (!top.resized(cell_size, r, err))
+                return MOSAIC_ERR_UNSUPPORTED;
+            top = r;
+        }
+        Group grp;
+        if (!grp.build(top, detail_percent, size_steps, err))
+            return MOSAIC_ERR_INVALID_ARGUMENT;
+        std::vector<GridStep> grid;
+        const EntropyEvaluator eval = bgr ? host_entropy_evaluator(grp, bgr, row_stride) : EntropyEvaluator();
+        if (!compute_grid_state(grp, rows, cols, eval, grid, err))
+            return MOSAIC_ERR_UNSUPPORTED;
+        if ((int)grid.size() > max_steps)
+            return MOSAIC_ERR_INVALID_ARGUMENT;
+        size_t used = 0;
+        for (size_t s = 0; s < grid.size(); ++s) {
+            if (used + grid[s].v.size() > out_capacity)
+                return MOSAIC_ERR_INVALID_ARGUMENT;
+            step_rows[s] = grid[s].rows;
+            step_cols[s] = grid[s].cols;
+            memcpy(out + used, grid[s].v.data(), grid[s].v.size() * sizeof(int64_t));
+            used += grid[s].v.size();
+        }
+        *n_steps = (int)grid.size();
+        return MOSAIC_OK;
+    } catch (const std::bad_alloc &) {
+        return MOSAIC_ERR_OUT_OF_MEMORY;
+    }
+}
 
 int mosaic_host_resize_area_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w)
 {

@@ -356,8 +356,8 @@ void merge_bounds(std::vector<Rect> &b)
 
 }  // namespace
 
-bool compute_grid_state(const Group &g, const uint8_t *main_bgr, int rows, int cols, size_t row_stride,
-                        std::vector<GridStep> &out, std::string &err)
+bool compute_grid_state(const Group &g, int rows, int cols, const EntropyEvaluator &evaluate, std::vector<GridStep> &out,
+                        std::string &err)
 {
     out.clear();
     if (g.cells.empty() || g.cells[0].empty()) {
@@ -366,19 +366,17 @@ bool compute_grid_state(const Group &g, const uint8_t *main_bgr, int rows, int c
     }
     const int gh = rows, gw = cols;
     std::vector<Rect> active{Rect{0, 0, gw, gh}}, next;
-    const double max_entropy = 8.0;  // ImageUtility::MAX_ENTROPY = log2(256)
     for (int step = 0; step <= g.size_steps && !active.empty(); ++step) {
         const Shape &shape = g.cells[step];
         const Shape &dshape = g.detail_cells[step];
-        const std::vector<uint8_t> dmasks = dshape.masks4();
         int gx, gy;
         grid_size(shape, gw, gh, kPadGrid, gx, gy);
         GridStep gs;
         gs.rows = gy;
         gs.cols = gx;
         gs.v.assign((size_t)gx * gy, -1);
-        next.clear();
-        std::vector<uint8_t> cell, small, gray, bmask;
+        // cells that intersect an active bound, raster order (findCellState, GridGenerator.cpp:113-140)
+        std::vector<EntropyCandidate> cand;
         for (int y = -kPadGrid; y < gy - kPadGrid; ++y)
             for (int x = -kPadGrid; x < gx - kPadGrid; ++x) {
                 const Rect r = rect_at(shape, x, y);
@@ -393,62 +391,69 @@ bool compute_grid_state(const Group &g, const uint8_t *main_bgr, int rows, int c
                 }
                 if (!in_bounds)
                     continue;
-                bool split = false;
-                if (main_bgr && step < g.size_steps) {
-                    Rect cg, local;
-                    const Rect db = detail_bound(shape, dshape.size, g.detail, x, y, gw, gh, &cg, &local);
-                    if (cg.w > 0 && cg.h > 0) {
-                        // visible part of the image, resized to the bounded detail mask's size
-                        cell.resize((size_t)cg.w * cg.h * 3);
-                        for (int yy = 0; yy < cg.h; ++yy)
-                            memcpy(&cell[(size_t)yy * cg.w * 3], main_bgr + (size_t)(cg.y + yy) * row_stride + (size_t)cg.x * 3,
-                                   (size_t)cg.w * 3);
-                        const uint8_t *img = cell.data();
-                        int ih = cg.h, iw = cg.w;
-                        if (!(cg.h == db.h && cg.w == db.w)) {
-                            // ImageUtility::resizeImage EXACT: factor from the height unless it is 1 (ImageUtility.cpp:40-48)
-                            double factor = (double)db.h / cg.h;
-                            if (factor == 1.0)
-                                factor = (double)db.w / cg.w;
-                            if (factor != 1.0) {
-                                if (factor > 1.0 || db.h > cg.h || db.w > cg.w) {
-                                    err = "grid state: cell up-scaling (INTER_CUBIC) is not implemented";
-                                    return false;
-                                }
-                                small.resize((size_t)db.w * db.h * 3);
-                                resize_area_u8(cell.data(), cg.h, cg.w, 3, small.data(), db.h, db.w);
-                                img = small.data();
-                                ih = db.h;
-                                iw = db.w;
-                            }
-                        }
-                        if (ih != db.h || iw != db.w) {
-                            err = "grid state: resized cell and mask bound disagree";
-                            return false;
-                        }
-                        gray.resize((size_t)ih * iw);
-                        bgr_to_gray_u8(img, (size_t)ih * iw, gray.data());
-                        bmask.resize((size_t)db.h * db.w);
-                        const uint8_t *m = dmasks.data() + (size_t)flip_at(shape, x, y) * dshape.size * dshape.size;
-                        for (int yy = 0; yy < db.h; ++yy)
-                            memcpy(&bmask[(size_t)yy * db.w], m + (size_t)(db.y + yy) * dshape.size + db.x, db.w);
-                        split = masked_entropy(gray.data(), bmask.data(), gray.size()) >= max_entropy * 0.7;
-                    }
+                EntropyCandidate c;
+                c.x = x;
+                c.y = y;
+                c.db = detail_bound(shape, dshape.size, g.detail, x, y, gw, gh, &c.cg, nullptr);
+                c.flip = flip_at(shape, x, y);
+                if (c.cg.w > 0 && c.cg.h > 0 && (c.db.h > c.cg.h || c.db.w > c.cg.w)) {
+                    err = "grid state: cell up-scaling (INTER_CUBIC) is not implemented";
+                    return false;
                 }
-                if (split) {
-                    const int y0 = clampi(r.y, 0, gh), y1 = clampi(r.y + r.h, 0, gh);
-                    const int x0 = clampi(r.x, 0, gw), x1 = clampi(r.x + r.w, 0, gw);
-                    if (y0 != y1 && x0 != x1)
-                        next.push_back(Rect{x0, y0, x1 - x0, y1 - y0});
-                } else
-                    gs.v[(size_t)(y + kPadGrid) * gx + (x + kPadGrid)] = 0;
+                cand.push_back(c);
             }
+        // entropy rule only below the last size step (GridGenerator.cpp:143)
+        std::vector<uint8_t> split(cand.size(), 0);
+        if (step < g.size_steps && evaluate && !cand.empty())
+            if (!evaluate(step, cand, split, err))
+                return false;
+        next.clear();
+        for (size_t i = 0; i < cand.size(); ++i) {
+            const EntropyCandidate &c = cand[i];
+            if (split[i] && c.cg.w > 0 && c.cg.h > 0) {
+                next.push_back(c.cg);  // the cell rect clamped to the image (GridGenerator.cpp:73-97)
+            } else if (!split[i]) {
+                gs.v[(size_t)(c.y + kPadGrid) * gx + (c.x + kPadGrid)] = 0;
+            }
+        }
         out.push_back(std::move(gs));
         active.swap(next);
         if (!active.empty())
             merge_bounds(active);
     }
     return true;
+}
+
+EntropyEvaluator host_entropy_evaluator(const Group &g, const uint8_t *main_bgr, size_t row_stride)
+{
+    return [&g, main_bgr, row_stride](int step, const std::vector<EntropyCandidate> &cand, std::vector<uint8_t> &split,
+                                      std::string &) -> bool {
+        const Shape &dshape = g.detail_cells[step];
+        const std::vector<uint8_t> dmasks = dshape.masks4();
+        std::vector<uint8_t> cell, small, gray, bmask;
+        for (size_t i = 0; i < cand.size(); ++i) {
+            const Rect &cg = cand[i].cg, &db = cand[i].db;
+            if (cg.w <= 0 || cg.h <= 0)
+                continue;  // empty image part: entropy 0 (ImageUtility.cpp:191-192)
+            cell.resize((size_t)cg.w * cg.h * 3);
+            for (int yy = 0; yy < cg.h; ++yy)
+                memcpy(&cell[(size_t)yy * cg.w * 3], main_bgr + (size_t)(cg.y + yy) * row_stride + (size_t)cg.x * 3, (size_t)cg.w * 3);
+            const uint8_t *img = cell.data();
+            if (!(cg.h == db.h && cg.w == db.w)) {  // ImageUtility::resizeImage EXACT (ImageUtility.cpp:40-48)
+                small.resize((size_t)db.w * db.h * 3);
+                resize_area_u8(cell.data(), cg.h, cg.w, 3, small.data(), db.h, db.w);
+                img = small.data();
+            }
+            gray.resize((size_t)db.h * db.w);
+            bgr_to_gray_u8(img, gray.size(), gray.data());
+            bmask.resize(gray.size());
+            const uint8_t *m = dmasks.data() + (size_t)cand[i].flip * dshape.size * dshape.size;
+            for (int yy = 0; yy < db.h; ++yy)
+                memcpy(&bmask[(size_t)yy * db.w], m + (size_t)(db.y + yy) * dshape.size + db.x, db.w);
+            split[i] = masked_entropy(gray.data(), bmask.data(), gray.size()) >= 8.0 * 0.7;  // MAX_ENTROPY * 0.7
+        }
+        return true;
+    };
 }
 
 }  // namespace mm

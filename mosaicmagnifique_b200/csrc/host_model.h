@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -71,7 +72,20 @@ struct GridStep {
     int rows = 0, cols = 0;
     std::vector<int64_t> v;
 };
-bool compute_grid_state(const Group &g, const uint8_t *main_bgr, int rows, int cols, size_t row_stride,
-                        std::vector<GridStep> &out, std::string &err);
+// one grid cell that lies inside an active bound: what the entropy rule needs to decide "split or keep"
+struct EntropyCandidate {
+    int x = 0, y = 0;  // unpadded grid coordinates
+    Rect cg;           // cell rect clamped to the image (the pixels the reference crops, GridGenerator.cpp:145-164)
+    Rect db;           // detail-space bound = size the crop is resized to and window of the detail mask (:166-185)
+    int flip = 0;      // mask index: flip_h + 2 * flip_v
+};
+// split[i] = 1 <=> masked grey-level entropy of candidate i >= 0.7 * 8 bits (GridGenerator.cpp:187-188)
+using EntropyEvaluator =
+    std::function<bool(int step, const std::vector<EntropyCandidate> &, std::vector<uint8_t> &split, std::string &err)>;
+// rows / cols: image size. A null evaluator never splits (what the reference does without a main image).
+bool compute_grid_state(const Group &g, int rows, int cols, const EntropyEvaluator &evaluate, std::vector<GridStep> &out,
+                        std::string &err);
+// the reference's host arithmetic (OpenCV-compatible INTER_AREA, BGR2GRAY, f64 entropy); the product uses the GPU evaluator
+EntropyEvaluator host_entropy_evaluator(const Group &g, const uint8_t *main_bgr, size_t row_stride);
 
 }  // namespace mm

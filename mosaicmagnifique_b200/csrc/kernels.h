@@ -85,6 +85,15 @@ cudaError_t launch_extract_cells(const float *mains, int H, int W, const CellDes
                                  AreaTab tab, const uint8_t *masks4, const int *pix_list, int n_active, int n_chunks,
                                  void *packed, PackLayout layout, cudaStream_t stream);
 
+// ---- grid_kernels.cu: entropy rule of GridGenerator::findCellState for a batch of candidate cells
+struct GridCandidate {
+    int cx, cy, cw, ch;  // cell rect clamped to the image
+    int bx, by, bw, bh;  // detail-space bound (resize target and mask window)
+    int flip;
+};
+cudaError_t launch_grid_entropy(const uint8_t *main_bgr, int W, const GridCandidate *cand, int n_cand, const uint8_t *masks4, int ds,
+                                double threshold, uint8_t *split, cudaStream_t stream);
+
 // ---- select_kernels.cu
 cudaError_t launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t stream);
 // D rows of V variants -> element-wise minimum into the first variant's rows

@@ -122,3 +122,37 @@ def test_cpp_mirror_compiles_and_links(tmp_path):
     rc = subprocess.call([exe])
     import torch
     assert rc == (0 if torch.cuda.is_available() else 3)
+
+
+@pytest.mark.parametrize("cell,detail,steps,shape_kind", [(64, 100, 2, "square"), (64, 50, 2, "square"), (48, 75, 1, "square"),
+                                                           (64, 50, 1, "hex")])
+def test_host_grid_state_matches_oracle(L, oracle, cell, detail, steps, shape_kind):
+    """GridGenerator::getGridState incl. the entropy split and mergeBounds: library host model vs the cv2-based oracle."""
+    pytest.importorskip("cv2")
+    from mosaicmagnifique_b200 import synthetic
+    from mosaicmagnifique_b200._capi import CellShapeC
+    main = synthetic.make_main_image(300, 420, 17, block=32)
+    if shape_kind == "hex":
+        sh = oracle.CellShape.from_mask(synthetic.hexagon_mask(cell))
+        sh.row_spacing = sh.alt_row_spacing = cell * 3 // 4
+        sh.col_spacing = sh.alt_col_spacing = cell * 55 // 64
+        sh.alt_row_offset = cell * 55 // 128
+        sh.alt_row_flip_h = True
+    else:
+        sh = oracle.CellShape.square(cell)
+    want = oracle.grid_state(oracle.CellGroup.make(sh, detail, steps), main)
+    c = CellShapeC(*sh.params())
+    n_steps = ctypes.c_int()
+    rows, cols = (ctypes.c_int * 8)(), (ctypes.c_int * 8)()
+    out = np.empty(1 << 16, np.int64)
+    rc = L.mosaic_host_grid_state(ctypes.byref(c), sh.mask.ctypes.data, 0, detail, steps, main.ctypes.data, main.shape[0], main.shape[1],
+                                  main.strides[0], 8, ctypes.byref(n_steps), rows, cols, out.ctypes.data, out.size)
+    assert rc == 0
+    assert n_steps.value == len(want)
+    off = 0
+    for s, w in enumerate(want):
+        assert (rows[s], cols[s]) == w.shape
+        got = out[off:off + w.size].reshape(w.shape)
+        assert np.array_equal(got, w), "step %d differs in %d cells" % (s, int((got != w).sum()))
+        off += w.size
+    assert sum(int((w >= 0).sum()) for w in want) > 10

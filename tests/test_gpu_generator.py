@@ -175,3 +175,33 @@ def test_colour_schemes_all_variants(oracle, scheme, diff):
     """The intended behaviour (quirk off): a cell takes the minimum over the original and every rotated variant."""
     main, lib = _inputs(95 + scheme, 200, 260, 50, 32)
     _run_case(oracle, main, lib, oracle.CellShape.square(32), diff, 100, 0, 2, 200, scheme=scheme, faithful=False)
+
+
+@pytest.mark.parametrize("cell,detail,steps,hexa", [(64, 100, 2, False), (64, 50, 2, False), (48, 75, 1, False), (64, 50, 1, True),
+                                                     (40, 30, 1, True)])
+def test_grid_state_on_gpu_matches_oracle(oracle, cell, detail, steps, hexa):
+    """mosaic_compute_grid_state: GridGenerator::getGridState with the entropy rule on the GPU (grid_kernels.cu) vs the
+    cv2-based oracle, incl. clipped border cells (non-square fractional INTER_AREA), flips and bound merging."""
+    from mosaicmagnifique_b200 import CellGroup, PhotomosaicGenerator, synthetic
+    main = synthetic.make_main_image(300, 420, 17, block=32)
+    if hexa:
+        sh = oracle.CellShape.from_mask(synthetic.hexagon_mask(cell))
+        sh.row_spacing = sh.alt_row_spacing = cell * 3 // 4
+        sh.col_spacing = sh.alt_col_spacing = cell * 55 // 64
+        sh.alt_row_offset = cell * 55 // 128
+        sh.alt_row_flip_h = True
+    else:
+        sh = oracle.CellShape.square(cell)
+    want = oracle.grid_state(oracle.CellGroup.make(sh, detail, steps), main)
+    gen = PhotomosaicGenerator(0)
+    gen.setMainImage(main)
+    cg = CellGroup()
+    cg.setCellShape(_to_product_shape(sh))
+    cg.setDetail(detail)
+    cg.setSizeSteps(steps)
+    gen.setCellGroup(cg)
+    got = gen.computeGridState()
+    gen.close()
+    assert len(got) == len(want)
+    for s, (a, b) in enumerate(zip(got, want)):
+        assert np.array_equal(a, b), "step %d: %d cells differ" % (s, int((a != b).sum()))

@@ -1,0 +1,102 @@
+"""Size-independent properties of the GPU path at sizes the CPU oracle cannot sweep (ragged tile edges, thousands of
+cells x hundreds of library images): library-permutation equivariance, planted exact matches, fused-argmin == D-argmin,
+repeat rule invariants. Through the reference-shaped API / C ABI."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _gen(main, lib, diff, rr=0, ra=0, cell=64, keep=True):
+    from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator
+    g = PhotomosaicGenerator(0)
+    g.setMainImage(main)
+    g.setLibrary(lib)
+    g.setColourDifference(diff)
+    cg = CellGroup()
+    cg.setCellShape(CellShape(cell))
+    g.setCellGroup(cg)
+    g.computeGridState()
+    g.setRepeat(rr, ra)
+    g.setKeepDifferences(keep)
+    assert g.generateBestFits()
+    return g
+
+
+@pytest.mark.parametrize("diff", [0, 2])
+def test_library_permutation_equivariance(diff):
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(1080, 1920, 5, block=64)
+    lib = synthetic.make_library(777, 64, 6)   # 777: ragged against both tile widths (8 and 64)
+    perm = np.random.default_rng(7).permutation(len(lib))
+    a = _gen(main, lib, diff)
+    b = _gen(main, lib[perm], diff)
+    Da, Db = a.getDifferences(0), b.getDifferences(0)
+    assert Da.shape == (30 * 17, 777)
+    assert np.array_equal(Db, Da[:, perm])        # same sums bit for bit wherever an image sits in a tile
+    ga, gb = a.getBestFits()[0], b.getBestFits()[0]
+    valid = ga >= 0
+    # argmin with lowest-index ties: compare through the score, not the index
+    ca = np.arange(valid.sum())
+    assert np.array_equal(Da[ca, ga[valid]], Db[ca, gb[valid]])
+    assert np.array_equal(Da[ca, ga[valid]], Da.min(axis=1))
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("diff", [0, 1, 2])
+def test_planted_exact_matches(diff):
+    """Cells copied verbatim into the library must come back with difference exactly 0 and win."""
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(640, 960, 8, block=64)
+    lib = synthetic.make_library(300, 64, 9)
+    planted = {}
+    rng = np.random.default_rng(10)
+    for k, (cy, cx) in enumerate([(0, 0), (3, 7), (9, 14), (5, 5)]):
+        j = int(rng.integers(0, len(lib)))
+        while j in planted.values():
+            j = int(rng.integers(0, len(lib)))
+        lib[j] = main[cy * 64:(cy + 1) * 64, cx * 64:(cx + 1) * 64]
+        planted[(cy, cx)] = j
+    g = _gen(main, lib, diff)
+    D = g.getDifferences(0)
+    grid = g.getBestFits()[0]
+    cols = 960 // 64
+    for (cy, cx), j in planted.items():
+        c = cy * cols + cx
+        assert D[c, j] == 0.0
+        assert grid[cy + 2, cx + 2] == j
+    assert (D >= 0).all() and np.isfinite(D).all()
+    g.close()
+
+
+def test_fused_argmin_equals_selection_on_D():
+    """No repeats -> the diff kernel's atomicMin epilogue decides; with a zero-addition repeat the wavefront kernel scans
+    the stored D matrix. Same winner everywhere (lowest index on ties)."""
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(1080, 1920, 11, block=64)
+    lib = synthetic.make_library(500, 64, 12)
+    lib[400:450] = lib[100:150]   # exact duplicates: ties must resolve to the lower index
+    a = _gen(main, lib, 2, 0, 0, keep=False)      # fused epilogue, D never written
+    b = _gen(main, lib, 2, 5, 0, keep=True)       # range > 0 but addition 0: selection kernel on D, no penalty
+    ga, gb = a.getBestFits()[0], b.getBestFits()[0]
+    assert np.array_equal(ga, gb)
+    assert not np.isin(ga, np.arange(400, 450)).any()
+    a.close(); b.close()
+
+
+def test_repeat_rule_invariants():
+    """With a huge addition no image may repeat inside the window of any earlier cell (library larger than the window)."""
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(1080, 1920, 13, block=64)
+    lib = synthetic.make_library(400, 64, 14)
+    r = 3
+    g = _gen(main, lib, 0, r, 100000000)
+    grid = g.getBestFits()[0]
+    rows, cols = grid.shape
+    for y in range(rows):
+        for x in range(cols):
+            if grid[y, x] < 0:
+                continue
+            win = np.concatenate([grid[max(0, y - r):y, max(0, x - r):x + r + 1].ravel(), grid[y, max(0, x - r):x]])
+            assert grid[y, x] not in win[win >= 0], (y, x)
+    g.close()
