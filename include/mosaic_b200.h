@@ -109,6 +109,10 @@ int mosaic_set_variant_quirk(mosaic_generator *g, int faithful);
 int mosaic_generate(mosaic_generator *g);
 /* out[r*cols+c] = library index, -1 = std::nullopt */
 int mosaic_get_best_fits(const mosaic_generator *g, int step, int64_t *out, int rows, int cols);
+/* buildPhotomosaic(const cv::Scalar &background) (PhotomosaicGeneratorBase.cpp:110-207): composites the chosen library images
+ * through the (flipped) cell masks into an 8U BGRA image of the main image's size, on the GPU. out: host or device pointer. */
+int mosaic_build_photomosaic(mosaic_generator *g, const uint8_t background_bgra[4], uint8_t *out_bgra, int rows, int cols,
+                             size_t row_stride);
 int mosaic_get_max_progress(const mosaic_generator *g);
 void mosaic_set_progress_callback(mosaic_generator *g, mosaic_progress_fn fn, void *user);
 void mosaic_cancel(mosaic_generator *g);

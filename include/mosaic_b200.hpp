@@ -157,6 +157,11 @@ public:
         }
         return out;
     }
+    // cv::Mat buildPhotomosaic(const cv::Scalar&): fills a rows x cols BGRA buffer (step = bytes per row)
+    void buildPhotomosaic(const uint8_t backgroundBGRA[4], uint8_t *outBGRA, int rows, int cols, size_t step)
+    {
+        ck(mosaic_build_photomosaic(m_g, backgroundBGRA, outBGRA, rows, cols, step));
+    }
     int getMaxProgress() { return mosaic_get_max_progress(m_g); }
     void cancel() { mosaic_cancel(m_g); }
     void setProgressCallback(mosaic_progress_fn fn, void *user) { mosaic_set_progress_callback(m_g, fn, user); }

@@ -970,6 +970,93 @@ int mosaic_get_timings(const mosaic_generator *g, mosaic_timings *out)
     return MOSAIC_OK;
 }
 
+// ---- buildPhotomosaic (PhotomosaicGeneratorBase.cpp:110-207)
+
+int mosaic_build_photomosaic(mosaic_generator *g, const uint8_t background_bgra[4], uint8_t *out_bgra, int rows, int cols, size_t row_stride)
+{
+    struct A {
+        const uint8_t *bg;
+        uint8_t *out;
+        int rows, cols;
+        size_t stride;
+    } a{background_bgra, out_bgra, rows, cols, row_stride};
+    return guard(g, "buildPhotomosaic", [](G *g, void *ap) {
+        A &a = *(A *)ap;
+        if (!a.bg || !a.out || a.rows != g->img_rows || a.cols != g->img_cols || a.stride < (size_t)a.cols * 4 || a.stride % 4 != 0)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "output must be a rows x cols BGRA buffer of the main image's size"};
+        if (g->grid.empty() || !g->have_group || g->n_lib == 0)
+            throw Fail{MOSAIC_ERR_NOT_READY, "no best fits to build from"};
+        if (g->lib_size != g->group.cells[0].size)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "library images must be at the cell size"};
+        cudaStream_t st = g->stream;
+        const int H = g->img_rows, W = g->img_cols, n_steps = (int)g->grid.size();
+        const int64_t N = g->n_lib;
+        DevBuf owner, out, d_steps;
+        std::vector<DevBuf> libs(n_steps), cells(n_steps), masks(n_steps);
+        std::vector<BuildStep> hsteps(n_steps);
+        owner.alloc((size_t)H * W * sizeof(unsigned long long), st);
+        CU(cudaMemsetAsync(owner.p, 0, owner.bytes, st));
+        const uint8_t *lib_prev = g->d_lib_u8.as<uint8_t>();
+        int S_prev = g->lib_size;
+        for (int s = 0; s < n_steps; ++s) {
+            const Shape &shape = g->group.cells[s];
+            const GridStep &gs = g->grid[s];
+            // library at this step: halved like batchResizeMat(libImg) (8U INTER_AREA, round(0.5 * size))
+            const uint8_t *lib_s = lib_prev;
+            int S = S_prev;
+            if (s > 0) {
+                S = (int)lround(0.5 * S_prev);
+                libs[s].alloc((size_t)N * S * S * 3, st);
+                if (S_prev % 2 == 0) {
+                    CU(launch_area_u8(lib_prev, libs[s].as<uint8_t>(), N, S_prev, 2, st));
+                } else {
+                    const AreaTable t = make_area_table(S_prev, S);
+                    DevBuf ts, tsi, ta;
+                    ts.alloc(t.start.size() * sizeof(int), st);
+                    tsi.alloc(t.si.size() * sizeof(int), st);
+                    ta.alloc(t.alpha.size() * sizeof(float), st);
+                    CU(cudaMemcpyAsync(ts.p, t.start.data(), ts.bytes, cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(tsi.p, t.si.data(), tsi.bytes, cudaMemcpyHostToDevice, st));
+                    CU(cudaMemcpyAsync(ta.p, t.alpha.data(), ta.bytes, cudaMemcpyHostToDevice, st));
+                    CU(launch_area_general_u8(lib_prev, libs[s].as<uint8_t>(), N, S_prev, S, AreaTab{ts.as<int>(), tsi.as<int>(), ta.as<float>()}, st));
+                    CU(cudaStreamSynchronize(st));
+                }
+                lib_s = libs[s].as<uint8_t>();
+            }
+            if (S != shape.size)
+                throw Fail{MOSAIC_ERR_UNSUPPORTED, "library and cell size disagree at step " + std::to_string(s) +
+                                                       " (the reference copies out of range here)"};
+            std::vector<BuildCell> hc;
+            for (int y = 0; y < gs.rows; ++y)
+                for (int x = 0; x < gs.cols; ++x) {
+                    const int64_t v = gs.v[(size_t)y * gs.cols + x];
+                    if (v < 0)
+                        continue;
+                    if (v >= N)
+                        throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "best fit index outside the library"};
+                    const Rect r = rect_at(shape, x - kPadGrid, y - kPadGrid);
+                    hc.push_back(BuildCell{r.x, r.y, flip_at(shape, x - kPadGrid, y - kPadGrid), (int)hc.size() + 1, (int)v});
+                }
+            const std::vector<uint8_t> m4 = shape.masks4();
+            masks[s].alloc(m4.size(), st);
+            CU(cudaMemcpyAsync(masks[s].p, m4.data(), m4.size(), cudaMemcpyHostToDevice, st));
+            cells[s].alloc(std::max<size_t>(hc.size(), 1) * sizeof(BuildCell), st);
+            CU(cudaMemcpyAsync(cells[s].p, hc.data(), hc.size() * sizeof(BuildCell), cudaMemcpyHostToDevice, st));
+            CU(launch_build_scatter(cells[s].as<BuildCell>(), (int)hc.size(), S, masks[s].as<uint8_t>(), H, W, s, n_steps,
+                                    owner.as<unsigned long long>(), st));
+            hsteps[s] = BuildStep{cells[s].as<BuildCell>(), lib_s, S};
+            lib_prev = lib_s;
+            S_prev = S;
+        }
+        d_steps.alloc(hsteps.size() * sizeof(BuildStep), st);
+        CU(cudaMemcpyAsync(d_steps.p, hsteps.data(), d_steps.bytes, cudaMemcpyHostToDevice, st));
+        out.alloc((size_t)H * W * 4, st);
+        CU(launch_build_gather(owner.as<unsigned long long>(), H, W, n_steps, d_steps.as<BuildStep>(), a.bg, out.as<uint8_t>(), (size_t)W, st));
+        CU(cudaMemcpy2DAsync(a.out, a.stride, out.p, (size_t)W * 4, (size_t)W * 4, H, cudaMemcpyDefault, st));
+        CU(cudaStreamSynchronize(st));
+    }, &a);
+}
+
 // ---- sharding
 
 int mosaic_set_shard(mosaic_generator *g, int rank, int world)

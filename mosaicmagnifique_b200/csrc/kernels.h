@@ -94,6 +94,23 @@ struct GridCandidate {
 cudaError_t launch_grid_entropy(const uint8_t *main_bgr, int W, const GridCandidate *cand, int n_cand, const uint8_t *masks4, int ds,
                                 double threshold, uint8_t *split, cudaStream_t stream);
 
+// ---- build_kernels.cu: buildPhotomosaic compositing
+struct BuildCell {
+    int x0, y0;      // top-left of the (unclipped) cell rect
+    int flip;        // mask index
+    int raster;      // 1-based raster index of the cell inside its step (0 = "no cell" in the owner map)
+    int lib_index;   // chosen library image
+};
+struct BuildStep {
+    const BuildCell *cells;  // indexed by raster - 1
+    const uint8_t *lib;      // 8U BGR library at this step's cell size, [N][S][S][3]
+    int S;
+};
+cudaError_t launch_build_scatter(const BuildCell *cells, int n_cells, int S, const uint8_t *masks4, int H, int W, int step, int n_steps,
+                                 unsigned long long *owner, cudaStream_t stream);
+cudaError_t launch_build_gather(const unsigned long long *owner, int H, int W, int n_steps, const BuildStep *steps, const uint8_t bgra[4],
+                                uint8_t *out, size_t out_stride_px, cudaStream_t stream);
+
 // ---- select_kernels.cu
 cudaError_t launch_fill_u64(unsigned long long *p, size_t n, unsigned long long v, cudaStream_t stream);
 // D rows of V variants -> element-wise minimum into the first variant's rows

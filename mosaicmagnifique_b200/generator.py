@@ -291,6 +291,14 @@ class PhotomosaicGenerator:
             out.append(g)
         return out
 
+    def buildPhotomosaic(self, backgroundColour=(0, 0, 0, 0)) -> np.ndarray:
+        """PhotomosaicGeneratorBase::buildPhotomosaic(const cv::Scalar&): H x W x 4 uint8 BGRA mosaic."""
+        rows, cols = self._main_shape
+        out = np.empty((rows, cols, 4), np.uint8)
+        bg = np.asarray(backgroundColour, np.uint8)
+        self._ck(self._L.mosaic_build_photomosaic(self._h, bg.ctypes.data, out.ctypes.data, rows, cols, out.strides[0]))
+        return out
+
     def getMaxProgress(self) -> int:
         return self._L.mosaic_get_max_progress(self._h)
 

@@ -557,3 +557,46 @@ def generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid
         if step + 1 < len(grid_states):
             lib_f32 = halve_library(lib_f32)
     return results
+
+
+# ----------------------------------------------------------------------------- buildPhotomosaic
+
+def build_photomosaic(main_shape, lib_bgr8: np.ndarray, group: CellGroup, grids: list, background=(0, 0, 0, 0)) -> np.ndarray:
+    """PhotomosaicGeneratorBase::buildPhotomosaic (PhotomosaicGeneratorBase.cpp:110-207): H x W x 4 uint8 BGRA."""
+    H, W = main_shape[:2]
+    bg = np.asarray(background, np.uint8)
+    mosaic = np.empty((H, W, 4), np.uint8)
+    mosaic[:] = bg
+    mosaic_mask = np.zeros((H, W), np.uint8)
+    lib = [cv2.cvtColor(im, cv2.COLOR_BGR2BGRA) for im in lib_bgr8]  # ImageUtility::addAlphaChannel
+    for step, grid in enumerate(grids):
+        if step != 0:
+            s = int(round(0.5 * lib[0].shape[0]))
+            lib = [resize_image_exact(im, s, s) for im in lib]  # batchResizeMat(libImg)
+        shape = group.cells[step]
+        masks4 = shape.masks4()
+        step_img = np.empty((H, W, 4), np.uint8)
+        step_img[:] = bg
+        step_mask = np.zeros((H, W), np.uint8)
+        rows, cols = grid.shape
+        for gy in range(rows):
+            for gx in range(cols):
+                if grid[gy, gx] < 0:
+                    continue
+                r = rect_at(shape, gx - PAD_GRID, gy - PAD_GRID)
+                y0, y1 = max(0, min(r[1], H)), max(0, min(r[1] + r[3], H))
+                x0, x1 = max(0, min(r[0], W)), max(0, min(r[0] + r[2], W))
+                if y0 == y1 or x0 == x1:
+                    continue
+                ly, lx = y0 - r[1], x0 - r[0]
+                m = masks4[flip_at(shape, gx - PAD_GRID, gy - PAD_GRID)][ly:ly + (y1 - y0), lx:lx + (x1 - x0)] != 0
+                src = lib[int(grid[gy, gx])][ly:ly + (y1 - y0), lx:lx + (x1 - x0)]
+                step_img[y0:y1, x0:x1][m] = src[m]
+                step_mask[y0:y1, x0:x1][m] = 255
+        if step != 0:
+            free = mosaic_mask == 0
+            mosaic[free] = step_img[free]
+            mosaic_mask[free] = step_mask[free]
+        else:
+            mosaic, mosaic_mask = step_img, step_mask
+    return mosaic
