@@ -17,7 +17,6 @@ from __future__ import annotations
 
 import ctypes
 import enum
-import struct
 
 import numpy as np
 
@@ -116,28 +115,16 @@ class CellShape:
 
 
 def load_mcs(path: str) -> CellShape:
-    """Reads a .mcs cell shape (CellShape::loadFromFile, CellShape.cpp:363-434): QDataStream big-endian
-    (Other/CustomQDataStream.h:56-87): u32 magic 0x87AECFB1, u32 version, QString name, PNG-encoded mask,
-    6 x i32 spacing/offset, 4 x bool flips. PNG decoding uses cv2 (host-side file format, not on the hot path)."""
-    import cv2
-    d = open(path, "rb").read()
-    magic, version = struct.unpack_from(">II", d, 0)
-    if magic != 0x87AECFB1:
-        raise ValueError("not a .mcs file")
-    o = 8
-    (n,) = struct.unpack_from(">I", d, o); o += 4
-    name = ""
-    if n != 0xFFFFFFFF:
-        name = d[o:o + n].decode("utf-16-be"); o += n
-    (n,) = struct.unpack_from(">I", d, o); o += 4
-    mask = cv2.imdecode(np.frombuffer(d[o:o + n], np.uint8), cv2.IMREAD_UNCHANGED); o += n
-    if mask.ndim == 3:
-        mask = np.ascontiguousarray(mask[..., 0])
-    vals = struct.unpack_from(">6i4?", d, o)
-    s = CellShape(mask)
-    (s.rowSpacing, s.colSpacing, s.alternateRowSpacing, s.alternateColSpacing, s.alternateRowOffset, s.alternateColOffset,
-     s.alternateColFlipHorizontal, s.alternateColFlipVertical, s.alternateRowFlipHorizontal, s.alternateRowFlipVertical) = vals
-    s.name = name
+    """Reads a .mcs cell shape (CellShape::loadFromFile, CellShape.cpp:363-434) through formats.load_mcs."""
+    from .formats import load_mcs as _load
+    f = _load(path)
+    s = CellShape(f["mask"])
+    s.rowSpacing, s.colSpacing = f["row_spacing"], f["col_spacing"]
+    s.alternateRowSpacing, s.alternateColSpacing = f["alt_row_spacing"], f["alt_col_spacing"]
+    s.alternateRowOffset, s.alternateColOffset = f["alt_row_offset"], f["alt_col_offset"]
+    s.alternateColFlipHorizontal, s.alternateColFlipVertical = f["alt_col_flip_h"], f["alt_col_flip_v"]
+    s.alternateRowFlipHorizontal, s.alternateRowFlipVertical = f["alt_row_flip_h"], f["alt_row_flip_v"]
+    s.name = f["name"]
     return s
 
 
