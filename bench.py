@@ -44,6 +44,11 @@ WORKLOADS = {
                        desc="config 4 scaled down (1920x1080 x 1,000 images) for quick runs"),
     "cfg4-med": dict(h=2160, w=3840, n_lib=2500, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
                      desc="config 4 scaled down (3840x2160 x 2,500 images) for kernel tuning"),
+    "cfg2": dict(h=4000, w=5000, n_lib=2000, cell=128, detail=50, diff=2, rr=0, ra=0, seed=1002, shape="hexagon",
+                 desc="synthetic 5000x4000 main x 2,000-image library, CIEDE2000, Hexagon cell shape (Hexagon.mcs geometry, "
+                      "alternate-row flips, clipped edge cells), cell 128, detail 50%"),
+    "cfg3": dict(h=2160, w=3840, n_lib=2000, cell=64, detail=100, diff=1, rr=0, ra=0, seed=1003, steps=2,
+                 desc="synthetic 4K (3840x2160) main x 2,000-image library, CIE76, 64px cells, 3 size levels (entropy sub-cell split)"),
     "cfg5": dict(h=8640, w=15360, n_lib=20000, cell=128, detail=50, diff=0, rr=0, ra=0, seed=1005,
                  desc="synthetic 16K main x 20,000-image library, RGB Euclidean, square cells at detail 50%"),
 }
@@ -107,11 +112,34 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU reference arm / baseline
 
+def make_shapes(cfg):
+    """(product CellShape, oracle CellShape) of a workload: square cells, or the reference's Hexagon.mcs geometry
+    (512 px mask, row spacing 385, column spacing 440, odd-row offset 220) resized to the cell size,
+    with alternate-row horizontal flips switched on so that flipped masks are exercised."""
+    from mosaicmagnifique_b200 import CellShape, synthetic
+    from oracle import oracle
+    if cfg.get("shape") == "hexagon":
+        o = oracle.CellShape.from_mask(synthetic.hexagon_mask(512))
+        o.row_spacing = o.alt_row_spacing = 385
+        o.col_spacing = o.alt_col_spacing = 440
+        o.alt_row_offset = 220
+        o.alt_row_flip_h = True
+        o = o.resized(cfg["cell"])
+    else:
+        o = oracle.CellShape.square(cfg["cell"])
+    p = CellShape(o.mask)
+    p.rowSpacing, p.colSpacing, p.alternateRowSpacing, p.alternateColSpacing = o.row_spacing, o.col_spacing, o.alt_row_spacing, o.alt_col_spacing
+    p.alternateRowOffset, p.alternateColOffset = o.alt_row_offset, o.alt_col_offset
+    p.alternateColFlipHorizontal, p.alternateColFlipVertical = o.alt_col_flip_h, o.alt_col_flip_v
+    p.alternateRowFlipHorizontal, p.alternateRowFlipVertical = o.alt_row_flip_h, o.alt_row_flip_v
+    return p, o
+
+
 def cpu_sample(cfg, main, lib, seconds):
     """Times the CPU oracle (plain-C restatement of CPUPhotomosaicGenerator, f64, early exit, 1 thread -- the reference
     generator is single-threaded) on a bounded sample of the workload: the first grid row(s) x a library prefix."""
     from oracle import oracle
-    og = oracle.CellGroup.make(oracle.CellShape.square(cfg["cell"]), cfg["detail"], 0)
+    og = oracle.CellGroup.make(make_shapes(cfg)[1], cfg["detail"], 0)  # sample = the top size level
     n_lib = min(len(lib), 64)
     sub_lib = lib[:n_lib]
     t0 = time.perf_counter()
@@ -215,8 +243,9 @@ def main():
 
     gen = PhotomosaicGenerator(local_rank)
     cg = CellGroup()
-    cg.setCellShape(CellShape(S))
+    cg.setCellShape(make_shapes(cfg)[0])
     cg.setDetail(cfg["detail"])
+    cg.setSizeSteps(cfg.get("steps", 0))
     gen.setColourDifference(cfg["diff"])
     gen.setCellGroup(cg)
     gen.setRepeat(cfg["rr"], cfg["ra"])
@@ -308,7 +337,7 @@ def main():
     sfu_rate = work["sfu"] * units_per_launch / diff_s              # reference-formula special-function ops / s
     flop_rate = work["flop"] * units_per_launch / diff_s
     ds = int(S * cfg["detail"] / 100)
-    min_bytes = (N * ds * ds * 16 + valid_cells * local_share * ds * ds * 20)  # library + cells read once (packed layout)
+    min_bytes = (N * ds * ds * 16 + valid_cells * local_share * ds * ds * 20)  # library + cells read once (packed layout, top level)
     roofline = {
         "bound": "mufu", "kernel": "diff_sum_kernel",
         "achieved": sfu_rate / 1e9, "peak": mb[2] / 1e9, "unit": "Gop/s", "frac": sfu_rate / mb[2],
