@@ -383,6 +383,21 @@ def main():
            "microbench": {"ffma_lane_ops_per_s": mb[0], "ffma2_lane_ops_per_s": mb[1], "mufu_rsq_per_s": mb[2], "mufu_ex2_per_s": mb[3],
                           "sm_count": int(mb[4]), "ciede_mix_pairs_per_s": mb[6]}}
 
+    if world == 1:
+        # tie band at full size (untimed): cells whose best two penalised candidates are within the FP32 tolerance
+        gen.setReportMargins(True)
+        gen.setGridState(state)
+        assert gen.generateBestFits()
+        n_tie = n_all = 0
+        for stp in range(len(state)):
+            b, s2 = gen.getMargins(stp)
+            n_all += len(b)
+            n_tie += int((((s2.astype(np.float64) - b) / np.maximum(b.astype(np.float64), 1e-30)) <= 1e-4).sum())
+        gen.setReportMargins(False)
+        out["tie_band"] = {"tolerance_relative": 1e-4, "cells": n_tie, "of": n_all,
+                           "note": "cells whose best and second-best penalised scores differ by <= 1e-4 relative: only there may "
+                                   "the FP32 engine and the f64 reference legitimately pick different images"}
+
     if not args.no_cpu_baseline and world == 1:
         cs = cpu_sample(cfg, main_np, lib_np, args.cpu_seconds)
         out["cpu_baseline"] = {"value": cs["nominal"] / cs["seconds"], "unit": "pixel-diffs/s", "cores": 1, "kind": "port",

@@ -123,6 +123,11 @@ int mosaic_set_keep_differences(mosaic_generator *g, int keep);
 int64_t mosaic_get_valid_cell_count(const mosaic_generator *g, int step);
 /* D[cell][lib] = min over variants of the masked difference sum (no repeat penalty), cells in raster order */
 int mosaic_get_differences(const mosaic_generator *g, int step, float *out, int64_t n_cells, int64_t n_lib);
+/* Tie-band reporting (BASELINE.json: cells whose best two candidates differ by less than the FP32 tolerance): when switched
+ * on, generate() records for every valid cell the best and the second-best PENALISED score it compared (the fused-argmin
+ * shortcut is bypassed). Raster order of the step's valid cells; unsharded handles only. */
+int mosaic_set_report_margins(mosaic_generator *g, int report);
+int mosaic_get_margins(const mosaic_generator *g, int step, float *best, float *second, int64_t n_cells);
 int mosaic_get_timings(const mosaic_generator *g, mosaic_timings *out);
 
 /* ---- multi-GPU sharding (no reference counterpart). One process per GPU:

@@ -73,6 +73,8 @@ def capi():
         "mosaic_set_keep_differences": (i, [vp, i]),
         "mosaic_get_valid_cell_count": (i64, [vp, i]),
         "mosaic_get_differences": (i, [vp, i, vp, i64, i64]),
+        "mosaic_set_report_margins": (i, [vp, i]),
+        "mosaic_get_margins": (i, [vp, i, vp, vp, i64]),
         "mosaic_get_timings": (i, [vp, c.POINTER(Timings)]),
         "mosaic_set_shard": (i, [vp, i, i]),
         "mosaic_generate_candidates": (i, [vp]),

@@ -135,6 +135,7 @@ struct mosaic_generator {
     std::vector<GridStep> grid;  // state in, best fits out
     int repeat_range = 0, repeat_addition = 0;
     bool keep_D = false;
+    bool report_margins = false;
     int rank = 0, world = 1;
 
     mosaic_progress_fn progress_fn = nullptr;
@@ -148,6 +149,8 @@ struct mosaic_generator {
     std::vector<StepPlan> plans;
     std::vector<DevBuf> d_D;            // per step [n_local_cells_pad * V][n_lib_pad]
     std::vector<DevBuf> d_cand_score, d_cand_idx;
+    std::vector<DevBuf> d_margins;      // per step [n_valid][2] when report_margins
+    std::vector<bool> have_margins;
     std::vector<int> cand_k;
     int V_eff = 1;
     mosaic_timings timings{};
@@ -444,6 +447,11 @@ void run_pipeline(G *g, bool candidates_only)
         g->d_cand_idx.resize(n_steps);
     }
     g->have_D.assign(n_steps, false);
+    if (g->d_margins.size() != n_steps) {
+        g->d_margins.clear();
+        g->d_margins.resize(n_steps);
+    }
+    g->have_margins.assign(n_steps, false);
     g->cand_k.assign(n_steps, 0);
 
     const bool penalise = g->repeat_range > 0 && g->repeat_addition != 0;
@@ -538,7 +546,7 @@ void run_pipeline(G *g, bool candidates_only)
 
         // ---- DiffReduce: one fused launch for the whole step
         t_diff.start();
-        const bool fused_argmin = !penalise && V == 1 && !candidates_only && g->world == 1;
+        const bool fused_argmin = !penalise && V == 1 && !candidates_only && g->world == 1 && !g->report_margins;
         const bool need_D = !fused_argmin || g->keep_D;
         DevBuf &D = g->d_D[s];
         if (need_D) {
@@ -601,9 +609,15 @@ void run_pipeline(G *g, bool candidates_only)
                 const int n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_all, select_max_ctas(g->device)));
                 d_counts.alloc((size_t)n_ctas * N * sizeof(int), st);
                 CU(cudaMemsetAsync(d_counts.p, 0, d_counts.bytes, st));
+                float *margins = nullptr;
+                if (g->report_margins) {
+                    g->d_margins[s].alloc(std::max<size_t>((size_t)n_all, 1) * 2 * sizeof(float), st);
+                    margins = g->d_margins[s].as<float>();
+                    g->have_margins[s] = true;
+                }
                 CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols,
                                  D.as<float>(), nullptr, (int)N, V * n_lib_pad, (int)N, g->repeat_range, g->repeat_addition,
-                                 d_prog.as<int>(), d_counts.as<int>(), n_ctas, nullptr, st));
+                                 d_prog.as<int>(), d_counts.as<int>(), n_ctas, margins, st));
                 if (n_all > 0)
                     tm.kernel_launches++;
             }
@@ -676,6 +690,7 @@ void mosaic_destroy(mosaic_generator *g)
     g->d_D.clear();
     g->d_cand_score.clear();
     g->d_cand_idx.clear();
+    g->d_margins.clear();
     if (g->stream) {
         cudaStreamSynchronize(g->stream);
         cudaStreamDestroy(g->stream);
@@ -960,6 +975,33 @@ int mosaic_get_differences(const mosaic_generator *g, int step, float *out, int6
     cudaError_t e = cudaMemcpy2D(out, (size_t)n_lib * sizeof(float), g->d_D[step].p, (size_t)g->V_eff * n_lib_pad * sizeof(float),
                                  (size_t)n_lib * sizeof(float), (size_t)n_local, cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? MOSAIC_OK : MOSAIC_ERR_CUDA;
+}
+
+int mosaic_set_report_margins(mosaic_generator *g, int report)
+{
+    if (!g)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    g->report_margins = report != 0;
+    return MOSAIC_OK;
+}
+
+int mosaic_get_margins(const mosaic_generator *g, int step, float *best, float *second, int64_t n_cells)
+{
+    if (!g || !best || !second || step < 0 || step >= (int)g->have_margins.size() || !g->have_margins[step])
+        return MOSAIC_ERR_NOT_READY;
+    if (n_cells != (int64_t)g->plans[step].cell_pos.size())
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    std::vector<float> m((size_t)n_cells * 2);
+    cudaSetDevice(g->device);
+    if (n_cells && cudaMemcpy(m.data(), g->d_margins[step].p, m.size() * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return MOSAIC_ERR_CUDA;
+    }
+    for (int64_t i = 0; i < n_cells; ++i) {
+        best[i] = m[2 * i];
+        second[i] = m[2 * i + 1];
+    }
+    return MOSAIC_OK;
 }
 
 int mosaic_get_timings(const mosaic_generator *g, mosaic_timings *out)

@@ -125,9 +125,10 @@ cudaError_t launch_topk(const float *D, int row_stride, int n_lib, int n_cells, 
 //   scores / idx : per cell M entries; idx == nullptr means "entry j is library image j" (rows of D, stride M_stride)
 //   row_progress : [rows] initialised to the column of the first valid cell of each row (cols if none)
 //   counts       : [n_ctas][n_lib] zero-filled scratch
+//   margins      : optional [n_cells][2] best / second-best penalised score of every cell
 cudaError_t launch_select(long long *grid, const int *cell_pos, const int *next_x, int n_cells, int rows, int cols,
                           const float *scores, const int *idx, int M, int M_stride, int n_lib, int repeat_range,
-                          int repeat_addition, int *row_progress, int *counts, int n_ctas, float *best_score,
+                          int repeat_addition, int *row_progress, int *counts, int n_ctas, float *margins,
                           cudaStream_t stream);
 int select_max_ctas(int device);
 // best_key (from the diff epilogue) -> grid

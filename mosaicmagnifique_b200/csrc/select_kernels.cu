@@ -196,7 +196,7 @@ struct SelArgs {
     int range, addition;
     int *row_progress;     // [rows], initialised to the column of the first valid cell (cols if none)
     int *counts;           // [gridDim.x][n_lib] zeroed scratch: occurrences of each library image in the window
-    float *best_score;     // optional [n_cells]: unpenalised score of the winner
+    float *margins;        // optional [n_cells][2]: best and second-best PENALISED score (tie-band reporting)
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p)
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelArgs a)
 {
     __shared__ double s_val[kSelThreads / 32];
     __shared__ int s_id[kSelThreads / 32];
-    __shared__ float s_raw[kSelThreads / 32];
+    __shared__ double s_second[kSelThreads / 32];
     int *cnt = a.counts + (size_t)blockIdx.x * a.n_lib;
     const int tid = threadIdx.x;
 
@@ -260,35 +260,38 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelArgs a)
         // ---- penalised argmin over this cell's entries
         const float *sc = a.scores + (size_t)c * a.M_stride;
         const int *ids = a.idx ? a.idx + (size_t)c * a.M : nullptr;
-        double best = DBL_MAX;
+        double best = DBL_MAX, second = DBL_MAX;
         int best_id = 0x7fffffff;
-        float best_raw = 0.0f;
         for (int j = tid; j < a.M; j += kSelThreads) {
             const int id = ids ? ids[j] : j;
             const float s = sc[j];
             const int k = penalise ? __ldcg(cnt + id) : 0;
             const double v = (double)s + (double)a.addition * (double)k;
             if (v < best || (v == best && id < best_id)) {
+                second = best;
                 best = v;
                 best_id = id;
-                best_raw = s;
+            } else if (v < second) {
+                second = v;
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const double ov = __shfl_xor_sync(0xffffffffu, best, o);
             const int oi = __shfl_xor_sync(0xffffffffu, best_id, o);
-            const float orw = __shfl_xor_sync(0xffffffffu, best_raw, o);
+            const double os = __shfl_xor_sync(0xffffffffu, second, o);
             if (ov < best || (ov == best && oi < best_id)) {
+                second = fmin(best, os);
                 best = ov;
                 best_id = oi;
-                best_raw = orw;
+            } else {
+                second = fmin(second, ov);
             }
         }
         if ((tid & 31) == 0) {
             s_val[tid >> 5] = best;
             s_id[tid >> 5] = best_id;
-            s_raw[tid >> 5] = best_raw;
+            s_second[tid >> 5] = second;
         }
         __syncthreads();
 
@@ -310,15 +313,19 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelArgs a)
         if (tid == 0) {
             for (int w = 1; w < kSelThreads / 32; ++w)
                 if (s_val[w] < best || (s_val[w] == best && s_id[w] < best_id)) {
+                    second = fmin(best, s_second[w]);
                     best = s_val[w];
                     best_id = s_id[w];
-                    best_raw = s_raw[w];
+                } else {
+                    second = fmin(second, s_val[w]);
                 }
             // DBL_MAX start + strict < as in the reference: NaN / inf rows leave the cell unset (nullopt)
             const long long result = (best < DBL_MAX && best_id != 0x7fffffff) ? (long long)best_id : -1ll;
             __stcg(a.grid + pos, result);
-            if (a.best_score)
-                a.best_score[c] = best_raw;
+            if (a.margins) {
+                a.margins[2 * c] = (float)best;
+                a.margins[2 * c + 1] = (float)second;
+            }
         }
         __syncthreads();  // count resets and the result are complete before the row counter moves
         if (tid == 0) {
@@ -330,13 +337,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelArgs a)
 
 cudaError_t launch_select(long long *grid, const int *cell_pos, const int *next_x, int n_cells, int rows, int cols,
                           const float *scores, const int *idx, int M, int M_stride, int n_lib, int repeat_range,
-                          int repeat_addition, int *row_progress, int *counts, int n_ctas, float *best_score,
+                          int repeat_addition, int *row_progress, int *counts, int n_ctas, float *margins,
                           cudaStream_t stream)
 {
     if (n_cells == 0)
         return cudaSuccess;
     SelArgs a{grid, cell_pos, next_x, n_cells, rows, cols, scores, idx, M, M_stride, n_lib, repeat_range, repeat_addition,
-              row_progress, counts, best_score};
+              row_progress, counts, margins};
     void *args[] = {&a};
     // cooperative launch: fails instead of deadlocking if the CTAs could not all be resident
     return cudaLaunchCooperativeKernel((void *)select_kernel, dim3(n_ctas), dim3(kSelThreads), args, 0, stream);

@@ -308,6 +308,16 @@ class PhotomosaicGenerator:
         self._ck(self._L.mosaic_get_differences(self._h, step, out.ctypes.data, n_cells, self._n_lib))
         return out
 
+    def setReportMargins(self, report: bool = True):
+        self._ck(self._L.mosaic_set_report_margins(self._h, int(report)))
+
+    def getMargins(self, step: int = 0):
+        """(best, second-best) penalised score of every valid cell of a step (tie-band reporting)."""
+        n = self._L.mosaic_get_valid_cell_count(self._h, step)
+        best, second = np.empty(n, np.float32), np.empty(n, np.float32)
+        self._ck(self._L.mosaic_get_margins(self._h, step, best.ctypes.data, second.ctypes.data, n))
+        return best, second
+
     def getTimings(self) -> dict:
         t = Timings()
         self._ck(self._L.mosaic_get_timings(self._h, ctypes.byref(t)))

@@ -100,3 +100,29 @@ def test_repeat_rule_invariants():
             win = np.concatenate([grid[max(0, y - r):y, max(0, x - r):x + r + 1].ravel(), grid[y, max(0, x - r):x]])
             assert grid[y, x] not in win[win >= 0], (y, x)
     g.close()
+
+
+def test_margins_report_best_and_second_best():
+    """Tie-band reporting: the recorded best / second-best penalised scores equal what the stored D matrix implies."""
+    from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator, synthetic
+    main = synthetic.make_main_image(640, 960, 31, block=64)
+    lib = synthetic.make_library(123, 64, 32)
+    lib[77] = lib[5]  # an exact tie somewhere in every row
+    g = PhotomosaicGenerator(0)
+    g.setMainImage(main)
+    g.setLibrary(lib)
+    g.setColourDifference(2)
+    cg = CellGroup()
+    cg.setCellShape(CellShape(64))
+    g.setCellGroup(cg)
+    g.computeGridState()
+    g.setKeepDifferences(True)
+    g.setReportMargins(True)
+    assert g.generateBestFits()   # no repeats: margins are plain best / second-best of each D row
+    D = g.getDifferences(0)
+    best, second = g.getMargins(0)
+    srt = np.sort(D, axis=1)
+    assert np.array_equal(best, srt[:, 0]) and np.array_equal(second, srt[:, 1])
+    grid = g.getBestFits()[0]
+    assert np.array_equal(grid[grid >= 0], D.argmin(axis=1))
+    g.close()
