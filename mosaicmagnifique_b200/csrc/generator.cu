@@ -615,9 +615,25 @@ void run_pipeline(G *g, bool candidates_only)
                     margins = g->d_margins[s].as<float>();
                     g->have_margins[s] = true;
                 }
-                CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols,
-                                 D.as<float>(), nullptr, (int)N, V * n_lib_pad, (int)N, g->repeat_range, g->repeat_addition,
-                                 d_prog.as<int>(), d_counts.as<int>(), n_ctas, margins, st));
+                // With a penalty the winner (and the runner-up) lies among the K (+1) smallest unpenalised scores
+                // (SURVEY.md 8e), so the wavefront scans candidate lists instead of whole D rows when that is shorter.
+                const int64_t r = g->repeat_range;
+                const int64_t k_need = std::min<int64_t>(N, 2 * r * r + 2 * r + 1 + (g->report_margins ? 1 : 0));
+                if (penalise && k_need * 4 <= N) {
+                    const int K = (int)k_need;
+                    g->d_cand_score[s].alloc((size_t)std::max<int64_t>(n_all, 1) * K * sizeof(float), st);
+                    g->d_cand_idx[s].alloc((size_t)std::max<int64_t>(n_all, 1) * K * sizeof(int), st);
+                    CU(launch_topk(D.as<float>(), V * n_lib_pad, (int)N, (int)n_all, K, g->d_cand_score[s].as<float>(),
+                                   g->d_cand_idx[s].as<int>(), st));
+                    tm.kernel_launches++;
+                    CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols,
+                                     g->d_cand_score[s].as<float>(), g->d_cand_idx[s].as<int>(), K, K, (int)N, g->repeat_range,
+                                     g->repeat_addition, d_prog.as<int>(), d_counts.as<int>(), n_ctas, margins, st));
+                } else {
+                    CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols,
+                                     D.as<float>(), nullptr, (int)N, V * n_lib_pad, (int)N, g->repeat_range, g->repeat_addition,
+                                     d_prog.as<int>(), d_counts.as<int>(), n_ctas, margins, st));
+                }
                 if (n_all > 0)
                     tm.kernel_launches++;
             }
