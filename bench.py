@@ -34,6 +34,10 @@ WORK = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1}, 1: {"flop": 9, "s
 # what this engine's kernel executes per pixel-difference (colour_math.cuh; instruction counts from SASS / ncu)
 EXECUTED = {2: {"mufu": 10, "fp32_lane_ops": 85}, 0: {"mufu": 1, "fp32_lane_ops": 7}, 1: {"mufu": 1, "fp32_lane_ops": 7}}
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the difference kernel, per launch on 1 GPU, from the ncu captures committed
+# under profiles/ (r1_dram_traffic_*_final.csv; final code of round 1). Not measurable inside an un-profiled run.
+NCU_TRAFFIC_BYTES = {"cfg4": 124474822144 + 205453312, "cfg5": 35904559360 + 13339392}
+
 WORKLOADS = {
     # name: (H, W, n_lib, cell, detail, diff, range, addition, seed)
     "cfg4": dict(h=4320, w=7680, n_lib=10000, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
@@ -341,7 +345,8 @@ def main():
     roofline = {
         "bound": "mufu", "kernel": "diff_sum_kernel",
         "achieved": sfu_rate / 1e9, "peak": mb[2] / 1e9, "unit": "Gop/s", "frac": sfu_rate / mb[2],
-        "traffic": None,
+        "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_dram_traffic_*_final.csv)",
         "note": "SURVEY 8d counts the REFERENCE formula: %d flop + %d special-function ops per pixel-diff; peak = MUFU.RSQ rate "
                 "measured live by the in-library micro-benchmark (16 lanes/clk/SM). The kernel's trig-free CIEDE2000 executes only "
                 "%d MUFU ops and %d FP32 lane-ops per pixel-diff, which is why frac can exceed 1; see executed_* (pipe utilisation "

@@ -74,14 +74,16 @@ __device__ __forceinline__ float comp(const float4 &v, int i) { return i == 0 ? 
 
 __global__ void __launch_bounds__(kEThreads, 2)
 diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char *__restrict__ lib, float *__restrict__ D,
-                   unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells)
+                   unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells,
+                   int n_cell_tiles, int n_lib_tiles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_bar[kEStages];
     __shared__ uint64_t empty_bar[kEStages];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cell_tile = blockIdx.x, lib_tile = blockIdx.y;
+    int cell_tile, lib_tile;
+    tile_of_block(blockIdx.x, n_cell_tiles, n_lib_tiles, cell_tile, lib_tile);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kEStages; ++s) {
@@ -175,15 +177,13 @@ cudaError_t launch_diff_euclid(const void *cells, const void *lib, float *D, uns
 {
     if (n_cell_tiles <= 0 || n_lib_tiles <= 0 || n_chunks <= 0)
         return cudaSuccess;
-    if (n_lib_tiles > 65535)
-        return cudaErrorInvalidValue;
     const size_t smem = (size_t)kEStages * kEStage;
     cudaError_t e = cudaFuncSetAttribute(diff_euclid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
-    dim3 grid(n_cell_tiles, n_lib_tiles);
+    const unsigned grid = (unsigned)n_cell_tiles * (unsigned)n_lib_tiles;  // 1-D, super-block rasterisation (kernels.h)
     diff_euclid_kernel<<<grid, kEThreads, smem, stream>>>((const unsigned char *)cells, (const unsigned char *)lib, D, best_key, n_chunks,
-                                                          n_lib, n_lib_tiles * MM_ETN, n_cells);
+                                                          n_lib, n_lib_tiles * MM_ETN, n_cells, n_cell_tiles, n_lib_tiles);
     return cudaGetLastError();
 }
 

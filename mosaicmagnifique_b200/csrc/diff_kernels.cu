@@ -80,14 +80,16 @@ constexpr uint32_t kStageBytes = kLibBlockBytes + kCellBlockBytes;
 template <int DIFF>
 __global__ void __launch_bounds__(kThreads, MM_MIN_CTAS)
 diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__restrict__ lib, float *__restrict__ D,
-                unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells)
+                unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells,
+                int n_cell_tiles, int n_lib_tiles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_bar[kStages];
     __shared__ uint64_t empty_bar[kStages];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cell_tile = blockIdx.x, lib_tile = blockIdx.y;
+    int cell_tile, lib_tile;
+    tile_of_block(blockIdx.x, n_cell_tiles, n_lib_tiles, cell_tile, lib_tile);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -194,9 +196,10 @@ static cudaError_t launch(const void *cells, const void *lib, float *D, unsigned
     cudaError_t e = cudaFuncSetAttribute(diff_sum_kernel<DIFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
         return e;
-    dim3 grid(n_cell_tiles, n_lib_tiles);
+    const unsigned grid = (unsigned)n_cell_tiles * (unsigned)n_lib_tiles;  // 1-D, super-block rasterisation (kernels.h)
     diff_sum_kernel<DIFF><<<grid, kThreads, smem, stream>>>((const unsigned char *)cells, (const unsigned char *)lib, D,
-                                                             best_key, n_chunks, n_lib, n_lib_tiles * MM_TNB, n_cells);
+                                                             best_key, n_chunks, n_lib, n_lib_tiles * MM_TNB, n_cells, n_cell_tiles,
+                                                             n_lib_tiles);
     return cudaGetLastError();
 }
 
@@ -205,8 +208,6 @@ cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, f
 {
     if (n_cell_tiles <= 0 || n_lib_tiles <= 0 || n_chunks <= 0)
         return cudaSuccess;
-    if (n_lib_tiles > 65535)
-        return cudaErrorInvalidValue;
     if (diff_type != MM_DIFF_CIEDE2000)
         return cudaErrorInvalidValue;  // RGB Euclidean / CIE76 run diff_euclid_kernel (diff_euclid.cu)
     return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream);
