@@ -234,6 +234,42 @@ Shape shape_params_only(const mosaic_cell_shape &c)
     return s;
 }
 
+// Phase timing without host synchronisation inside the pipeline: every begin/end pair records two CUDA events on the
+// launching stream; the sums are read after the call's final stream synchronise.
+struct PhaseClock {
+    cudaStream_t s;
+    std::vector<cudaEvent_t> ev;  // start, stop, start, stop, ...
+    std::vector<int> phase;
+    explicit PhaseClock(cudaStream_t st) : s(st) {}
+    ~PhaseClock()
+    {
+        for (cudaEvent_t e : ev)
+            cudaEventDestroy(e);
+    }
+    void begin(int ph)
+    {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ev.push_back(a);
+        ev.push_back(b);
+        phase.push_back(ph);
+        cudaEventRecord(a, s);
+    }
+    void end() { cudaEventRecord(ev.back(), s); }
+    double sum(int ph)  // call after the stream has been synchronised
+    {
+        double t = 0;
+        for (size_t i = 0; i < phase.size(); ++i)
+            if (phase[i] == ph) {
+                float m = 0;
+                cudaEventElapsedTime(&m, ev[2 * i], ev[2 * i + 1]);
+                t += m;
+            }
+        return t;
+    }
+};
+
 struct Timer {
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t s;
@@ -385,8 +421,8 @@ void run_pipeline(G *g, bool candidates_only)
     const int n_lib_tiles = (int)((N + tg.tnb - 1) / tg.tnb);
     const int n_lib_pad = n_lib_tiles * tg.tnb;
     const size_t n_steps = g->grid.size();
-    Timer t_pre(st), t_diff(st), t_sel(st);
-    double pre_ms = 0, diff_ms = 0, sel_ms = 0;
+    PhaseClock clock(st);
+    enum { kPre = 0, kDiff = 1, kSel = 2 };
 
     if (!g->d_lut.p) {
         g->d_lut.alloc(33 * 33 * 33 * 3 * sizeof(int16_t), st);
@@ -395,20 +431,38 @@ void run_pipeline(G *g, bool candidates_only)
     }
 
     // ---- Preprocess: main image -> working space (PhotomosaicGeneratorBase.cpp:223-252)
-    t_pre.start();
+    clock.begin(kPre);
     DevBuf &d_main_f32 = g->ws.main_f32;
     const size_t n_main_px = (size_t)g->img_rows * g->img_cols;
     d_main_f32.alloc((size_t)V * n_main_px * 3 * sizeof(float), st);
-    for (int v = 0; v < V; ++v) {
-        const uint8_t *src = g->d_main_u8.as<uint8_t>();
+    // a sharded rank only reads the image rows its own cells cover: convert just those (whole rows, so the hue rotation
+    // keeps OpenCV's per-row SIMD / tail split)
+    int row_lo = g->img_rows, row_hi = 0;
+    for (size_t s = 0; s < n_steps; ++s) {
+        const StepPlan &p = g->plans[s];
+        const Shape &normal = g->group.cells[s];
+        for (int64_t c = p.cell_begin; c < p.cell_end; ++c) {
+            const int pos = p.cell_pos[c];
+            const Rect r = rect_at(normal, pos % p.cols - kPadGrid, pos / p.cols - kPadGrid);
+            row_lo = std::min(row_lo, std::max(r.y, 0));
+            row_hi = std::max(row_hi, std::min(r.y + r.h, g->img_rows));
+        }
+    }
+    if (row_hi < row_lo)
+        row_lo = row_hi = 0;
+    const int n_rows_conv = row_hi - row_lo;
+    const size_t row_off_px = (size_t)row_lo * g->img_cols;
+    for (int v = 0; v < V && n_rows_conv > 0; ++v) {
+        const uint8_t *src = g->d_main_u8.as<uint8_t>() + row_off_px * 3;
         if (rotations[v] != 0.0f) {
             g->ws.main_var_u8.alloc(n_main_px * 3, st);
-            CU(launch_hue_rotate(src, g->ws.main_var_u8.as<uint8_t>(), g->img_rows, g->img_cols, rotations[v], st));
+            CU(launch_hue_rotate(src, g->ws.main_var_u8.as<uint8_t>() + row_off_px * 3, n_rows_conv, g->img_cols, rotations[v], st));
             tm.kernel_launches++;
-            src = g->ws.main_var_u8.as<uint8_t>();
+            src = g->ws.main_var_u8.as<uint8_t>() + row_off_px * 3;
         }
-        CU(launch_to_working_space(src, (size_t)g->img_cols * 3, g->img_rows, g->img_cols, d_main_f32.as<float>() + (size_t)v * n_main_px * 3,
-                                   is_lab, g->d_lut.as<int16_t>(), nullptr, st));
+        CU(launch_to_working_space(src, (size_t)g->img_cols * 3, n_rows_conv, g->img_cols,
+                                   d_main_f32.as<float>() + ((size_t)v * n_main_px + row_off_px) * 3, is_lab, g->d_lut.as<int16_t>(),
+                                   nullptr, st));
         tm.kernel_launches++;
     }
 
@@ -435,8 +489,7 @@ void run_pipeline(G *g, bool candidates_only)
                                    d_lib_work.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
         tm.kernel_launches++;
     }
-    t_pre.stop();
-    pre_ms += t_pre.ms();
+    clock.end();
 
     if (g->d_D.size() != n_steps) {
         g->d_D.clear();
@@ -467,7 +520,7 @@ void run_pipeline(G *g, bool candidates_only)
         const int ds = p.ds, P = ds * ds;
         Workspace &d = g->ws;
 
-        t_pre.start();
+        clock.begin(kPre);
         if (s > 0) {
             // halve the working-space library (CPUPhotomosaicGenerator.cpp:95-99)
             DevBuf &half = g->ws.lib_half;
@@ -541,11 +594,10 @@ void run_pipeline(G *g, bool candidates_only)
                                 p.k, cell_tab, d.masks4.as<uint8_t>(), d.pix_list.as<int>(), p.n_active, p.n_chunks,
                                 d.cells_packed.p, layout, st));
         tm.kernel_launches++;
-        t_pre.stop();
-        pre_ms += t_pre.ms();
+        clock.end();
 
         // ---- DiffReduce: one fused launch for the whole step
-        t_diff.start();
+        clock.begin(kDiff);
         const bool fused_argmin = !penalise && V == 1 && !candidates_only && g->world == 1 && !g->report_margins;
         const bool need_D = !fused_argmin || g->keep_D;
         DevBuf &D = g->d_D[s];
@@ -568,11 +620,10 @@ void run_pipeline(G *g, bool candidates_only)
                                   (int)N, n_rows_local, st));
         if (n_cell_tiles > 0)
             tm.kernel_launches++;
-        t_diff.stop();
-        diff_ms += t_diff.ms();
+        clock.end();
 
         // ---- Repeats + FindLowest
-        t_sel.start();
+        clock.begin(kSel);
         if (V > 1 && need_D) {
             CU(launch_min_variants(D.as<float>(), (int)n_local, V, n_lib_pad, st));
             tm.kernel_launches++;
@@ -640,19 +691,19 @@ void run_pipeline(G *g, bool candidates_only)
             CU(cudaMemcpyAsync(gs.v.data(), d_grid.p, gs.v.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
             tm.d2h_bytes += (double)(gs.v.size() * sizeof(long long));
         }
-        t_sel.stop();
-        sel_ms += t_sel.ms();
-        CU(cudaStreamSynchronize(st));
-
-        // progress(int): the reference emits per cell with weight 4^(steps-1-step) (CPUPhotomosaicGenerator.cpp:55, 87-88)
+        clock.end();
+        // progress(int): the reference emits per cell with weight 4^(steps-1-step) (CPUPhotomosaicGenerator.cpp:55, 87-88);
+        // here once per finished size step (the only point where the host waits inside the pipeline, and only if asked)
         progress += (int)(pow(4.0, (double)(n_steps - 1 - s)) * p.rows * p.cols);
-        if (g->progress_fn)
+        if (g->progress_fn) {
+            CU(cudaStreamSynchronize(st));
             g->progress_fn(progress, g->progress_user);
+        }
     }
     CU(cudaStreamSynchronize(st));
-    tm.preprocess_ms = pre_ms;
-    tm.diff_ms = diff_ms;
-    tm.select_ms = sel_ms;
+    tm.preprocess_ms = clock.sum(kPre);
+    tm.diff_ms = clock.sum(kDiff);
+    tm.select_ms = clock.sum(kSel);
     tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
 }
 
