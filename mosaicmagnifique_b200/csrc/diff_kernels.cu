@@ -10,7 +10,7 @@
 //
 // Data layout (built by prep_kernels.cu):
 //   lib  : float4 (x0,x1,x2,-)  [lib_tile][chunk][TNB][KP]   one contiguous 16 KB block per (tile, chunk)
-//          CIEDE2000: half-scale channels (L/2-25, a/2, b/2, C/2), w = 2, and image PAIRS interleaved for the packed
+//          CIEDE2000: stored-scale channels (L/2-25, a/50, b/50, C/50), w = 50, and image PAIRS interleaved for the packed
 //          FP32 path: [lib_tile][chunk][TNB/2][2][KP] float4 = (L0,L1,a0,a1) then (b0,b1,C0,C1)
 //   cell : float4 (x0,x1,x2,C)  [cell_tile][chunk][TCB][KP]  followed by float w[TCB][KP] -> 20 KB block
 //   w = 1 where the (flipped) detail mask is set and the pixel lies inside the cell's detail-space bound,
@@ -142,7 +142,7 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
                 for (int i = 0; i < MM_TNB / 2; ++i) {
                     const float4 la = lib_s[(i * 2 + 0) * MM_KP + p];
                     const float4 lb = lib_s[(i * 2 + 1) * MM_KP + p];
-                    const mm_f2 d = mm_ciede2000_half_v<mm_f2>(c.x, c.y, c.z, c.w, mm_f2{la.x, la.y}, mm_f2{la.z, la.w},
+                    const mm_f2 d = mm_ciede2000_stored_v<mm_f2>(c.x, c.y, c.z, c.w, mm_f2{la.x, la.y}, mm_f2{la.z, la.w},
                                                                mm_f2{lb.x, lb.y}, mm_f2{lb.z, lb.w});
                     const mm_f2 a2 = v_fma(mm_f2{w, w}, d, mm_f2{acc[2 * i], acc[2 * i + 1]});
                     acc[2 * i] = a2.x;

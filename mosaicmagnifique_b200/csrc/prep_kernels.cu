@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "colour_math.cuh"
 #include "kernels.h"
 
 namespace mm {
@@ -313,10 +314,10 @@ __device__ __forceinline__ float chroma_of(float a, float b)
     return (float)sqrt((double)a * (double)a + (double)b * (double)b);
 }
 
-// CIEDE2000 channels as colour_math.cuh wants them: (L/2 - 25, a/2, b/2, C/2)
+// CIEDE2000 channels as colour_math.cuh wants them: (L/2 - 25, a/50, b/50, C/50)
 __device__ __forceinline__ float4 half_scale_lab(float L, float a, float b)
 {
-    return make_float4(fmaf(0.5f, L, -25.0f), 0.5f * a, 0.5f * b, 0.5f * chroma_of(a, b));
+    return make_float4(fmaf(0.5f, L, -25.0f), MM_CIEDE_AB_SCALE * a, MM_CIEDE_AB_SCALE * b, MM_CIEDE_AB_SCALE * chroma_of(a, b));
 }
 
 __global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
@@ -419,9 +420,9 @@ __global__ void extract_cells_kernel(const float *__restrict__ mains, int H, int
         unsigned char *blk = packed + (tile * n_chunks + chunk) * block_bytes;
         reinterpret_cast<float4 *>(blk)[ti * MM_KP + pi] =
             with_chroma ? half_scale_lab(v[0], v[1], v[2]) : make_float4(v[0], v[1], v[2], 0.0f);
-        // the CIEDE2000 kernel returns dE/2 (half-scale channels): the factor 2 lives in the weight
+        // the CIEDE2000 kernel returns dE/50 (stored-scale channels): the factor lives in the weight
         reinterpret_cast<float *>(blk + (size_t)MM_TCB * MM_KP * 16)[ti * MM_KP + pi] =
-            (in_bound && active) ? (with_chroma ? 2.0f : 1.0f) : 0.0f;
+            (in_bound && active) ? (with_chroma ? MM_CIEDE_WEIGHT : 1.0f) : 0.0f;
     }
 }
 

@@ -29,11 +29,12 @@ void cm_ciede2000_batch_x2(const float *a, const float *b, long n, float *out)
         const float c1 = (float)sqrt((double)p[1] * p[1] + (double)p[2] * p[2]);
         const float c20 = (float)sqrt((double)q0[1] * q0[1] + (double)q0[2] * q0[2]);
         const float c21 = (float)sqrt((double)q1[1] * q1[1] + (double)q1[2] * q1[2]);
-        const mm_f2 L2{fmaf(0.5f, q0[0], -25.0f), fmaf(0.5f, q1[0], -25.0f)}, a2{0.5f * q0[1], 0.5f * q1[1]},
-            b2{0.5f * q0[2], 0.5f * q1[2]}, C2{0.5f * c20, 0.5f * c21};
-        const mm_f2 r = mm_ciede2000_half_v<mm_f2>(fmaf(0.5f, p[0], -25.0f), 0.5f * p[1], 0.5f * p[2], 0.5f * c1, L2, a2, b2, C2);
-        out[i] = 2.0f * r.x;
-        out[i + 1] = 2.0f * r.y;
+        const float sc = MM_CIEDE_AB_SCALE;
+        const mm_f2 L2{fmaf(0.5f, q0[0], -25.0f), fmaf(0.5f, q1[0], -25.0f)}, a2{sc * q0[1], sc * q1[1]}, b2{sc * q0[2], sc * q1[2]},
+            C2{sc * c20, sc * c21};
+        const mm_f2 r = mm_ciede2000_stored_v<mm_f2>(fmaf(0.5f, p[0], -25.0f), sc * p[1], sc * p[2], sc * c1, L2, a2, b2, C2);
+        out[i] = MM_CIEDE_WEIGHT * r.x;
+        out[i + 1] = MM_CIEDE_WEIGHT * r.y;
     }
 }
 }

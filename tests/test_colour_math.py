@@ -108,7 +108,7 @@ def test_euclid_random_vs_oracle(cm, oracle):
 
 
 def test_packed_form_equals_scalar_form(cm):
-    """mm_ciede2000_half_v<mm_f2> (the FFMA2 kernel path: one cell pixel against two library pixels) is the same source as
+    """mm_ciede2000_stored_v<mm_f2> (the FFMA2 kernel path: one cell pixel against two library pixels) is the same source as
     the scalar form; on the CPU both must agree bit for bit."""
     rng = np.random.default_rng(9)
     n = 1 << 16
