@@ -164,6 +164,15 @@ int mosaic_kernel_bgr_to_lab(int device, const uint8_t *bgr, int64_t n_pixels, f
 int mosaic_kernel_hue_rotate(int device, const uint8_t *bgr, int rows, int cols, float rotation_degrees, uint8_t *out);
 int mosaic_kernel_resize_area_u8(int device, const uint8_t *src, int64_t n, int size, int k, uint8_t *dst);
 int mosaic_kernel_resize_area_f32(int device, const float *src, int64_t n, int size, int k, float *dst);
+int mosaic_kernel_resize_cubic_u8(int device, const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w);
+
+/* ---- library ingest: ImageLibrary::addImage (ImageLibrary/ImageLibrary.cpp:62-86) minus the container bookkeeping.
+ * Centre crop to a square (ImageUtility::imageToSquare CROP, Other/ImageUtility.cpp:249-267), then
+ * ImageUtility::resizeImage EXACT to image_size (Other/ImageUtility.cpp:34-62: INTER_AREA when shrinking, INTER_CUBIC when
+ * growing, a plain copy when the side already matches) -- crop upload, resize and download on the GPU.
+ * bgr: 8U BGR rows x cols with row_stride bytes per row; out: image_size x image_size x 3, contiguous.
+ * MOSAIC_ERR_INVALID_ARGUMENT for an empty image (std::invalid_argument in the reference, ImageLibrary.cpp:65-66). */
+int mosaic_library_ingest(int device, const uint8_t *bgr, int rows, int cols, size_t row_stride, int image_size, uint8_t *out);
 /* FP32 / MUFU pipe-rate micro-benchmark (roofline denominators): out[0] FFMA lane-ops/s, [1] FFMA2 lane-ops/s,
  * [2] MUFU.RSQ ops/s, [3] MUFU.EX2 ops/s, [4] SM count, [5] cycles per 16-FFMA loop iteration, and (n_out >= 9) the rate of a
  * synthetic loop in the CIEDE2000 kernel's instruction proportions, in "pixel pairs"/s: [6] 42 FFMA2 + 10 MUFU + 10 ALU,
@@ -182,6 +191,9 @@ int mosaic_host_grid_state(const mosaic_cell_shape *shape, const uint8_t *mask, 
                            int *step_cols, int64_t *out, size_t out_capacity);
 /* cv::resize(INTER_AREA) for 8U images with cn channels (OpenCV-compatible, any down-scaling ratio) */
 int mosaic_host_resize_area_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w);
+/* cv::resize(INTER_CUBIC) for 8U images with cn channels, as OpenCV's own (non-IPP) code computes it: what
+ * ImageUtility::resizeImage uses when growing (Other/ImageUtility.cpp:50-51); CellShape::resized mask growth goes through it */
+int mosaic_host_resize_cubic_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -88,6 +88,82 @@ private:
     int m_detail = 100, m_steps = 0;
 };
 
+// ImageLibrary (src/ImageLibrary/ImageLibrary.h:9-66): the container that feeds setLibrary. addImage's centre crop and
+// EXACT resize (ImageLibrary.cpp:62-86) run on the GPU through mosaic_library_ingest; .mil files are read and written by
+// the Python layer (mosaicmagnifique_b200/formats.py), not here.
+class ImageLibrary {
+public:
+    explicit ImageLibrary(size_t imageSize, int device = 0) : m_imageSize(imageSize), m_device(device) {}
+
+    void setImageSize(size_t size)  // ImageLibrary.cpp:42-52
+    {
+        if (size == m_imageSize)
+            return;
+        m_imageSize = size;
+        for (size_t i = 0; i < m_originalImages.size(); ++i)
+            m_resizedImages[i] = ingest(Image{m_originalImages[i].data(), m_originalSize[i], m_originalSize[i],
+                                              static_cast<size_t>(m_originalSize[i]) * 3});
+    }
+    size_t getImageSize() const { return m_imageSize; }
+
+    // the reference inserts at an index drawn from std::random_device (ImageLibrary.cpp:75-78); pass the index to choose it
+    size_t addImage(const Image &im, const std::string &name = std::string(), size_t index = static_cast<size_t>(-1))
+    {
+        if (!im.data || im.rows <= 0 || im.cols <= 0)
+            throw std::invalid_argument("t_im was empty.");
+        if (index > m_names.size())
+            index = m_names.size();
+        std::vector<uint8_t> img = ingest(im);
+        m_names.insert(m_names.begin() + index, name);
+        m_originalSize.insert(m_originalSize.begin() + index, static_cast<int>(m_imageSize));
+        m_originalImages.insert(m_originalImages.begin() + index, img);  // addImageInternal, ImageLibrary.cpp:240-244
+        m_resizedImages.insert(m_resizedImages.begin() + index, std::move(img));
+        return index;
+    }
+    const std::vector<std::string> &getNames() const { return m_names; }
+    const std::vector<std::vector<uint8_t>> &getImages() const { return m_resizedImages; }  // each imageSize x imageSize x 3
+    void removeAtIndex(size_t i)
+    {
+        m_names.erase(m_names.begin() + i);
+        m_originalSize.erase(m_originalSize.begin() + i);
+        m_originalImages.erase(m_originalImages.begin() + i);
+        m_resizedImages.erase(m_resizedImages.begin() + i);
+    }
+    void clear()
+    {
+        m_names.clear();
+        m_originalSize.clear();
+        m_originalImages.clear();
+        m_resizedImages.clear();
+    }
+    // contiguous [N][size][size][3] block for PhotomosaicGenerator::setLibrary
+    std::vector<uint8_t> packed() const
+    {
+        std::vector<uint8_t> out;
+        out.reserve(m_resizedImages.size() * m_imageSize * m_imageSize * 3);
+        for (const auto &im : m_resizedImages)
+            out.insert(out.end(), im.begin(), im.end());
+        return out;
+    }
+
+private:
+    std::vector<uint8_t> ingest(const Image &im) const
+    {
+        std::vector<uint8_t> out(m_imageSize * m_imageSize * 3);
+        const int rc = mosaic_library_ingest(m_device, im.data, im.rows, im.cols, im.step, static_cast<int>(m_imageSize), out.data());
+        if (rc == MOSAIC_ERR_INVALID_ARGUMENT)
+            throw std::invalid_argument("t_im was empty.");
+        if (rc != MOSAIC_OK)
+            throw std::runtime_error("mosaic_library_ingest failed (CUDA)");
+        return out;
+    }
+    size_t m_imageSize;
+    int m_device;
+    std::vector<std::string> m_names;
+    std::vector<int> m_originalSize;
+    std::vector<std::vector<uint8_t>> m_originalImages, m_resizedImages;
+};
+
 // CUDAPhotomosaicGenerator(const int device): the only back-end; there is no CPU fallback.
 class PhotomosaicGenerator {
 public:

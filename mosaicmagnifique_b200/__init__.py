@@ -8,6 +8,7 @@ and no CPU fallback: importing works anywhere, creating a generator needs the li
 from ._capi import MosaicError, capi, library_path  # noqa: F401
 from .generator import (CIE76, CIEDE2000, RGB_EUCLIDEAN, CellGroup, CellShape, ColourDifference, ColourScheme,  # noqa: F401
                         PhotomosaicGenerator, load_mcs)
+from .library import ImageLibrary  # noqa: F401
 
-__all__ = ["PhotomosaicGenerator", "CellShape", "CellGroup", "ColourDifference", "ColourScheme", "MosaicError", "capi",
+__all__ = ["PhotomosaicGenerator", "ImageLibrary", "CellShape", "CellGroup", "ColourDifference", "ColourScheme", "MosaicError", "capi",
            "library_path", "load_mcs", "RGB_EUCLIDEAN", "CIE76", "CIEDE2000"]

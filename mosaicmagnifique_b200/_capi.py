@@ -95,6 +95,9 @@ def capi():
         "mosaic_flip_at": (i, [shp, i, i]),
         "mosaic_host_grid_state": (i, [shp, vp, i, i, i, vp, i, i, sz, i, ip, ip, ip, vp, sz]),
         "mosaic_host_resize_area_u8": (i, [vp, i, i, i, vp, i, i]),
+        "mosaic_host_resize_cubic_u8": (i, [vp, i, i, i, vp, i, i]),
+        "mosaic_kernel_resize_cubic_u8": (i, [i, vp, i, i, i, vp, i, i]),
+        "mosaic_library_ingest": (i, [i, vp, i, i, sz, i, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header and library disagree

@@ -119,6 +119,66 @@ bool resize_area_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, in
     return true;
 }
 
+// ------------------------------------------------------------------ INTER_CUBIC (8U)
+//
+// cv::resize(..., INTER_CUBIC) for 8U as OpenCV's own code computes it (imgproc/resize.cpp: interpolateCubic with
+// A = -0.75 in float, coefficients rounded to 11-bit fixed point, horizontal pass in int, vertical pass
+// VResizeCubicVec_32s8u in float for the first (row elements / 8) * 8 elements of a row and FixedPtCast integer
+// arithmetic for the row tail). Probed against cv2 4.13 with IPP switched off (cv2.ipp.setUseIPP(False)): IPP builds
+// replace this function by a closed float kernel whose results differ by +-1 LSB in ~5 % of the samples.
+CubicTable make_cubic_table(int ssize, int dsize)
+{
+    CubicTable t;
+    t.idx.resize((size_t)dsize * 4);
+    t.coef.resize((size_t)dsize * 4);
+    const double scale = 1.0 / ((double)dsize / ssize);  // resize(): scale_x = 1. / inv_scale_x
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        const int s0 = (int)floorf(f);
+        f -= (float)s0;
+        const float A = -0.75f;
+        float c[4];
+        c[0] = ((A * (f + 1) - 5 * A) * (f + 1) + 8 * A) * (f + 1) - 4 * A;
+        c[1] = ((A + 2) * f - (A + 3)) * f * f + 1;
+        c[2] = ((A + 2) * (1 - f) - (A + 3)) * (1 - f) * (1 - f) + 1;
+        c[3] = 1.f - c[0] - c[1] - c[2];
+        for (int k = 0; k < 4; ++k) {
+            t.idx[(size_t)d * 4 + k] = std::min(std::max(s0 - 1 + k, 0), ssize - 1);  // border: replicate
+            t.coef[(size_t)d * 4 + k] = (int16_t)std::min(std::max(lrintf(c[k] * 2048.0f), -32768L), 32767L);
+        }
+    }
+    return t;
+}
+
+bool resize_cubic_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw)
+{
+    if (sh <= 0 || sw <= 0 || dh <= 0 || dw <= 0 || cn <= 0)
+        return false;
+    const CubicTable xt = make_cubic_table(sw, dw), yt = make_cubic_table(sh, dh);
+    const int row = dw * cn, n_vec = row / 8 * 8;
+    std::vector<int> h((size_t)sh * row);
+    for (int y = 0; y < sh; ++y)
+        for (int x = 0; x < dw; ++x)
+            for (int c = 0; c < cn; ++c) {
+                int v = 0;
+                for (int k = 0; k < 4; ++k)
+                    v += src[((size_t)y * sw + xt.idx[(size_t)x * 4 + k]) * cn + c] * xt.coef[(size_t)x * 4 + k];
+                h[(size_t)y * row + x * cn + c] = v;
+            }
+    const float scale = 1.0f / (2048.0f * 2048.0f);
+    for (int y = 0; y < dh; ++y) {
+        const int *S[4];
+        int16_t b[4];
+        for (int k = 0; k < 4; ++k) {
+            S[k] = h.data() + (size_t)yt.idx[(size_t)y * 4 + k] * row;
+            b[k] = yt.coef[(size_t)y * 4 + k];
+        }
+        for (int i = 0; i < row; ++i)
+            dst[(size_t)y * row + i] = cubic_vertical_u8(S[0][i], S[1][i], S[2][i], S[3][i], b, scale, i < n_vec);
+    }
+    return true;
+}
+
 void bgr_to_gray_u8(const uint8_t *bgr, size_t n, uint8_t *gray)
 {
     // OpenCV RGB2Gray<uchar>: 15-bit fixed point, B 3735, G 19235, R 9798 (probed against cv2 4.13)
@@ -173,16 +233,16 @@ bool Shape::resized(int new_size, Shape &out, std::string &err) const
         out = *this;
         return true;
     }
-    if (new_size > size) {
-        err = "cell mask up-scaling (INTER_CUBIC) is not implemented; supply a mask at least as large as the cell size";
-        return false;
-    }
     if (new_size < 1) {
         err = "cell size must be >= 1";
         return false;
     }
+    // ImageUtility::resizeImage (ImageUtility.cpp:34-62): INTER_AREA when shrinking, INTER_CUBIC when growing
     std::vector<uint8_t> rm((size_t)new_size * new_size);
-    resize_area_u8(mask.data(), size, size, 1, rm.data(), new_size, new_size);
+    if (new_size > size)
+        resize_cubic_u8(mask.data(), size, size, 1, rm.data(), new_size, new_size);
+    else
+        resize_area_u8(mask.data(), size, size, 1, rm.data(), new_size, new_size);
     out = Shape();
     out.set_mask(rm.data(), new_size);  // CellShape(const cv::Mat&) -> setCellMask -> threshold
     const double ratio = (double)new_size / size;

@@ -5,6 +5,7 @@
 //   GridGenerator  src/Grid/GridGenerator.{h,cpp}    (valid / split decision per cell), GridBounds
 // plus the OpenCV arithmetic those use on the host (INTER_AREA for 8U, BGR2GRAY, entropy).
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #include <functional>
@@ -62,6 +63,47 @@ struct AreaTable {
     std::vector<float> alpha;
 };
 AreaTable make_area_table(int ssize, int dsize);
+
+// cv::resize(..., INTER_CUBIC) for 8U, cn channels, as OpenCV's own (non-IPP) code computes it: per destination sample the
+// four clamped source indices and the 11-bit fixed-point cubic coefficients (A = -0.75)
+struct CubicTable {
+    std::vector<int> idx;       // [dsize][4]
+    std::vector<int16_t> coef;  // [dsize][4]
+};
+CubicTable make_cubic_table(int ssize, int dsize);
+bool resize_cubic_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw);
+// vertical pass of one sample from the four horizontally filtered rows (int, scaled by 2^11): the first (row / 8) * 8
+// elements of a row go through OpenCV's float SIMD path (unfused mul + add, round half to even), the tail through the
+// fixed-point cast. Shared by the host implementation and the CUDA kernel.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint8_t cubic_vertical_u8(int s0, int s1, int s2, int s3, const int16_t b[4], float scale, bool vec_path)
+{
+    int r;
+    if (vec_path) {
+        const float b0 = (float)b[0] * scale, b1 = (float)b[1] * scale, b2 = (float)b[2] * scale, b3 = (float)b[3] * scale;
+#if defined(__CUDA_ARCH__)
+        float v = __fmul_rn((float)s3, b3);
+        v = __fadd_rn(__fmul_rn((float)s2, b2), v);
+        v = __fadd_rn(__fmul_rn((float)s1, b1), v);
+        v = __fadd_rn(__fmul_rn((float)s0, b0), v);
+        r = __float2int_rn(v);
+#else
+        volatile float v = (float)s3 * b3;  // volatile: no contraction, every product and sum rounded on its own
+        volatile float p = (float)s2 * b2;
+        v = p + v;
+        p = (float)s1 * b1;
+        v = p + v;
+        p = (float)s0 * b0;
+        v = p + v;
+        r = (int)lrintf(v);
+#endif
+    } else {
+        r = (s0 * b[0] + s1 * b[1] + s2 * b[2] + s3 * b[3] + (1 << 21)) >> 22;
+    }
+    return (uint8_t)(r < 0 ? 0 : r > 255 ? 255 : r);
+}
 
 // cvtColor(COLOR_BGR2GRAY) for 8U (OpenCV fixed point) and ImageUtility::calculateEntropy (ImageUtility.cpp:189-242)
 void bgr_to_gray_u8(const uint8_t *bgr, size_t n, uint8_t *gray);

@@ -283,6 +283,102 @@ int mosaic_kernel_resize_area_f32(int device, const float *src, int64_t n, int s
     return MOSAIC_OK;
 }
 
+namespace {
+struct CubicDev {
+    Dev idx, coef;
+    CubicTab tab{};
+    cudaError_t upload(const CubicTable &t)
+    {
+        cudaError_t e = idx.alloc(t.idx.size() * sizeof(int));
+        if (e == cudaSuccess)
+            e = coef.alloc(t.coef.size() * sizeof(int16_t));
+        if (e == cudaSuccess)
+            e = cudaMemcpy(idx.p, t.idx.data(), t.idx.size() * sizeof(int), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(coef.p, t.coef.data(), t.coef.size() * sizeof(int16_t), cudaMemcpyHostToDevice);
+        tab = CubicTab{idx.as<int>(), coef.as<int16_t>()};
+        return e;
+    }
+};
+
+// device image (contiguous, cn channels) -> device image of another size with the reference's choice of filter
+// (ImageUtility::resizeImage: INTER_AREA when shrinking, INTER_CUBIC when growing); square, 3 channels for INTER_AREA
+int resize_like_reference(const uint8_t *d_src, int side, uint8_t *d_dst, int new_side)
+{
+    if (new_side < side) {
+        if (side % new_side == 0) {
+            KCHECK(launch_area_u8(d_src, d_dst, 1, side, side / new_side, 0));
+        } else {
+            const AreaTable t = make_area_table(side, new_side);
+            Dev ts, tsi, ta;
+            KCHECK(ts.alloc(t.start.size() * sizeof(int)));
+            KCHECK(tsi.alloc(t.si.size() * sizeof(int)));
+            KCHECK(ta.alloc(t.alpha.size() * sizeof(float)));
+            KCHECK(cudaMemcpy(ts.p, t.start.data(), t.start.size() * sizeof(int), cudaMemcpyHostToDevice));
+            KCHECK(cudaMemcpy(tsi.p, t.si.data(), t.si.size() * sizeof(int), cudaMemcpyHostToDevice));
+            KCHECK(cudaMemcpy(ta.p, t.alpha.data(), t.alpha.size() * sizeof(float), cudaMemcpyHostToDevice));
+            KCHECK(launch_area_general_u8(d_src, d_dst, 1, side, new_side, AreaTab{ts.as<int>(), tsi.as<int>(), ta.as<float>()}, 0));
+            KCHECK(cudaDeviceSynchronize());  // the tables die with this scope
+        }
+    } else {
+        CubicDev xt;
+        KCHECK(xt.upload(make_cubic_table(side, new_side)));
+        KCHECK(launch_cubic_u8(d_src, side, side, 3, d_dst, new_side, new_side, xt.tab, xt.tab, 0));
+        KCHECK(cudaDeviceSynchronize());
+    }
+    return MOSAIC_OK;
+}
+}  // namespace
+
+int mosaic_kernel_resize_cubic_u8(int device, const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w)
+{
+    if (!src || !dst || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || cn <= 0)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    if (int rc = use_device(device))
+        return rc;
+    Dev d_in, d_out;
+    CubicDev xt, yt;
+    KCHECK(d_in.alloc((size_t)src_h * src_w * cn));
+    KCHECK(d_out.alloc((size_t)dst_h * dst_w * cn));
+    KCHECK(cudaMemcpy(d_in.p, src, (size_t)src_h * src_w * cn, cudaMemcpyHostToDevice));
+    KCHECK(xt.upload(make_cubic_table(src_w, dst_w)));
+    KCHECK(yt.upload(make_cubic_table(src_h, dst_h)));
+    KCHECK(launch_cubic_u8(d_in.as<uint8_t>(), src_h, src_w, cn, d_out.as<uint8_t>(), dst_h, dst_w, xt.tab, yt.tab, 0));
+    KCHECK(cudaMemcpy(dst, d_out.p, (size_t)dst_h * dst_w * cn, cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
+int mosaic_host_resize_cubic_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w)
+{
+    if (!src || !dst)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    return resize_cubic_u8(src, src_h, src_w, cn, dst, dst_h, dst_w) ? MOSAIC_OK : MOSAIC_ERR_INVALID_ARGUMENT;
+}
+
+int mosaic_library_ingest(int device, const uint8_t *bgr, int rows, int cols, size_t row_stride, int image_size, uint8_t *out)
+{
+    if (!bgr || !out || rows <= 0 || cols <= 0 || image_size <= 0 || row_stride < (size_t)cols * 3)
+        return MOSAIC_ERR_INVALID_ARGUMENT;  // empty image: std::invalid_argument, ImageLibrary.cpp:65-66
+    if (int rc = use_device(device))
+        return rc;
+    // ImageUtility::imageToSquare, CROP (ImageUtility.cpp:255-267): keep the centre square, offset = (long - short) / 2
+    const int side = std::min(rows, cols);
+    const int y0 = cols < rows ? (rows - cols) / 2 : 0, x0 = cols > rows ? (cols - rows) / 2 : 0;
+    const uint8_t *crop = bgr + (size_t)y0 * row_stride + (size_t)x0 * 3;
+    Dev d_in, d_out;
+    KCHECK(d_in.alloc((size_t)side * side * 3));
+    KCHECK(cudaMemcpy2D(d_in.p, (size_t)side * 3, crop, row_stride, (size_t)side * 3, side, cudaMemcpyHostToDevice));
+    if (side == image_size) {  // resizeFactor == 1: the image itself (ImageUtility.cpp:47-48)
+        KCHECK(cudaMemcpy(out, d_in.p, (size_t)side * side * 3, cudaMemcpyDeviceToHost));
+        return MOSAIC_OK;
+    }
+    KCHECK(d_out.alloc((size_t)image_size * image_size * 3));
+    if (int rc = resize_like_reference(d_in.as<uint8_t>(), side, d_out.as<uint8_t>(), image_size))
+        return rc;
+    KCHECK(cudaMemcpy(out, d_out.p, (size_t)image_size * image_size * 3, cudaMemcpyDeviceToHost));
+    return MOSAIC_OK;
+}
+
 int mosaic_kernel_microbench(int device, double *out, int n_out)
 {
     if (!out || n_out < 6)

@@ -92,6 +92,13 @@ cudaError_t launch_area_general_u8(const uint8_t *src, uint8_t *dst, int64_t n, 
                                    cudaStream_t stream);
 cudaError_t launch_area_general_f32(const float *src, float *dst, int64_t n, int src_size, int dst_size, AreaTab tab,
                                     cudaStream_t stream);
+// INTER_CUBIC for 8U, cn channels, one image (library ingest, mask growth): device copies of host_model's CubicTable
+struct CubicTab {
+    const int *idx;        // [dst_size][4] clamped source indices
+    const int16_t *coef;   // [dst_size][4] 11-bit fixed-point coefficients
+};
+cudaError_t launch_cubic_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw, CubicTab xt, CubicTab yt,
+                            cudaStream_t stream);
 // working f32 AoS library [n][P][3] -> packed float4 tiles (compacted pixel order, chroma in .w)
 cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
                                 int n_chunks, int n_lib_tiles, PackLayout layout, cudaStream_t stream);

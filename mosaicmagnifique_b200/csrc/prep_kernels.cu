@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "colour_math.cuh"
+#include "host_model.h"
 #include "kernels.h"
 
 namespace mm {
@@ -303,6 +304,45 @@ cudaError_t launch_area_general_f32(const float *src, float *dst, int64_t n, int
     if (total == 0)
         return cudaSuccess;
     area_general_f32_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, dst, n, src_size, dst_size, tab);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ INTER_CUBIC (8U), library ingest / mask growth
+//
+// cv::resize(..., INTER_CUBIC) as OpenCV's own code computes it (host_model.cpp: make_cubic_table / resize_cubic_u8):
+// one thread per destination element, 16 taps; the vertical pass is host_model.h's cubic_vertical_u8, shared with the host.
+__global__ void cubic_u8_kernel(const uint8_t *__restrict__ src, int sw, int cn, uint8_t *__restrict__ dst, int dh, int dw,
+                                CubicTab xt, CubicTab yt)
+{
+    const int row = dw * cn, n_vec = row / 8 * 8;
+    const size_t total = (size_t)dh * row;
+    const float scale = 1.0f / (2048.0f * 2048.0f);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(i % row), y = (int)(i / row);
+        const int x = e / cn, c = e % cn;
+        int h[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint8_t *S = src + (size_t)yt.idx[y * 4 + r] * sw * cn + c;
+            int v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                v += (int)S[(size_t)xt.idx[x * 4 + k] * cn] * (int)xt.coef[x * 4 + k];
+            h[r] = v;
+        }
+        const int16_t b[4] = {yt.coef[y * 4], yt.coef[y * 4 + 1], yt.coef[y * 4 + 2], yt.coef[y * 4 + 3]};
+        dst[i] = cubic_vertical_u8(h[0], h[1], h[2], h[3], b, scale, e < n_vec);
+    }
+}
+
+cudaError_t launch_cubic_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t *dst, int dh, int dw, CubicTab xt, CubicTab yt,
+                            cudaStream_t stream)
+{
+    (void)sh;
+    const size_t total = (size_t)dh * dw * cn;
+    if (total == 0)
+        return cudaSuccess;
+    cubic_u8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, sw, cn, dst, dh, dw, xt, yt);
     return cudaGetLastError();
 }
 

@@ -92,10 +92,10 @@ class CellShape:
         if size == self.getSize():
             return self._copy()
         L = capi()
-        if size > self.getSize():
-            raise MosaicError(-5, "cell mask up-scaling (INTER_CUBIC) is not implemented")
         out = np.empty((size, size), np.uint8)
-        rc = L.mosaic_host_resize_area_u8(self._mask.ctypes.data, self.getSize(), self.getSize(), 1, out.ctypes.data, size, size)
+        # ImageUtility::resizeImage (ImageUtility.cpp:50-51): INTER_AREA when shrinking, INTER_CUBIC when growing
+        fn = L.mosaic_host_resize_cubic_u8 if size > self.getSize() else L.mosaic_host_resize_area_u8
+        rc = fn(self._mask.ctypes.data, self.getSize(), self.getSize(), 1, out.ctypes.data, size, size)
         if rc:
             raise MosaicError(rc, "resize failed")
         r = CellShape(out)

@@ -139,8 +139,21 @@ def resize_image_exact(img: np.ndarray, th: int, tw: int) -> np.ndarray:
         factor = tw / img.shape[1]
     if factor == 1.0:
         return img
-    flags = cv2.INTER_AREA if factor < 1 else cv2.INTER_CUBIC
-    return cv2.resize(img, (tw, th), interpolation=flags)
+    if factor < 1:
+        return cv2.resize(img, (tw, th), interpolation=cv2.INTER_AREA)
+    return resize_cubic_opencv(img, th, tw)
+
+
+def resize_cubic_opencv(img: np.ndarray, th: int, tw: int) -> np.ndarray:
+    """cv::resize(INTER_CUBIC) by OpenCV's OWN code (imgproc/resize.cpp). IPP-enabled builds (this cv2 is one) route 8U
+    cubic through a closed IPP kernel whose results differ by +-1 LSB in ~5 % of the samples from OpenCV's code, so IPP
+    is switched off around the call: the parity target is the open, reproducible implementation."""
+    was = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        return cv2.resize(img, (tw, th), interpolation=cv2.INTER_CUBIC)
+    finally:
+        cv2.ipp.setUseIPP(was)
 
 
 @dataclass

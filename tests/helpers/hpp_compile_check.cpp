@@ -10,8 +10,14 @@ int main()
     using namespace mosaicb200;
     try {
         PhotomosaicGenerator generator(0);
-        std::vector<uint8_t> img(64 * 96 * 3, 100), lib(5 * 32 * 32 * 3, 90);
+        std::vector<uint8_t> img(64 * 96 * 3, 100), big(50 * 70 * 3, 90);
         generator.setMainImage(Image{img.data(), 64, 96, 96 * 3});
+        ImageLibrary library(32);  // ImageLibrary lib(cellSize), Benchmark_Generator.h:50
+        for (int i = 0; i < 5; ++i) {
+            big[i] = static_cast<uint8_t>(40 * i);
+            library.addImage(Image{big.data(), 50, 70, 70 * 3}, "image");
+        }
+        const std::vector<uint8_t> lib = library.packed();
         generator.setLibrary(lib.data(), 5, 32);
         generator.setColourDifference(ColourDifference::Type::CIEDE2000);
         generator.setColourScheme(ColourScheme::Type::NONE);

@@ -111,6 +111,64 @@ def test_host_resize_area_non_square(L):
     assert np.array_equal(out, cv2.resize(a, (64, 20), interpolation=cv2.INTER_AREA))
 
 
+@pytest.mark.parametrize("sh,sw,dh,dw,cn", [(50, 50, 128, 128, 3), (100, 100, 128, 128, 3), (127, 127, 128, 128, 1), (64, 64, 128, 128, 3),
+                                            (37, 37, 64, 64, 1), (3, 3, 10, 10, 3), (1, 1, 5, 5, 1), (20, 31, 45, 77, 3),
+                                            (255, 255, 301, 301, 3), (9, 9, 27, 27, 1)])
+def test_host_resize_cubic_matches_opencv(L, oracle, sh, sw, dh, dw, cn):
+    """INTER_CUBIC (ImageUtility::resizeImage when growing, ImageUtility.cpp:50-51) bit-exact against OpenCV's own code
+    (IPP off: oracle.resize_cubic_opencv says why), including the float-SIMD / fixed-point split of the vertical pass."""
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(sh * 1000 + dw)
+    a = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+    out = np.empty((dh, dw, cn), np.uint8)
+    assert L.mosaic_host_resize_cubic_u8(a.ctypes.data, sh, sw, cn, out.ctypes.data, dh, dw) == 0
+    ref = oracle.resize_cubic_opencv(a, dh, dw).reshape(dh, dw, cn)
+    assert np.array_equal(out, ref)
+
+
+def test_cell_shape_growth_matches_oracle(oracle):
+    """CellShape::resized to a LARGER size (CellShape.cpp:281-312 -> INTER_CUBIC -> threshold) on the library's host model."""
+    pytest.importorskip("cv2")
+    from mosaicmagnifique_b200 import CellShape
+    yy, xx = np.mgrid[0:48, 0:48]
+    mask = (((yy - 23.5) ** 2 + (xx - 20.0) ** 2) < 19.0 ** 2).astype(np.uint8) * 255
+    for new in (64, 100, 129):
+        ours = CellShape(mask)
+        ours.rowSpacing, ours.alternateRowOffset = 40, 13
+        r = ours.resized(new)
+        o = oracle.CellShape.from_mask(mask)
+        o.row_spacing, o.alt_row_offset = 40, 13
+        ro = o.resized(new)
+        assert np.array_equal(r.getCellMask(), ro.mask)
+        assert (r.rowSpacing, r.colSpacing, r.alternateRowOffset) == (ro.row_spacing, ro.col_spacing, ro.alt_row_offset)
+
+
+def test_image_library_container_round_trip(tmp_path):
+    """ImageLibrary save / load / operator== / removeAtIndex / clear (ImageLibrary.cpp:15-39, 100-236): host bookkeeping,
+    no device needed (addImage's crop + resize is GPU work, tests/test_gpu_kernels.py)."""
+    from mosaicmagnifique_b200 import ImageLibrary
+    from mosaicmagnifique_b200.formats import save_mil
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (5, 16, 16, 3), dtype=np.uint8)
+    path = str(tmp_path / "a.mil")
+    save_mil(path, imgs, ["n%d" % i for i in range(5)])
+    lib = ImageLibrary(99)
+    lib.loadFromFile(path)
+    assert lib.getImageSize() == 16 and lib.getNames() == ["n%d" % i for i in range(5)]
+    assert np.array_equal(lib.asArray(), imgs)
+    path2 = str(tmp_path / "b.mil")
+    lib.saveToFile(path2)
+    lib2 = ImageLibrary(1)
+    lib2.loadFromFile(path2)
+    assert lib == lib2
+    lib2.removeAtIndex(1)
+    assert lib != lib2 and lib2.getNames() == ["n0", "n2", "n3", "n4"]
+    lib2.clear()
+    assert lib2.asArray().shape == (0, 16, 16, 3)
+    with pytest.raises(ValueError):
+        lib.saveToFile("")
+
+
 def test_cpp_mirror_compiles_and_links(tmp_path):
     """include/mosaic_b200.hpp (the C++ host mirror of the reference classes) builds against the C ABI; the program
     itself needs a GPU (exit 3 = clean 'no device' error, 0 = ran)."""

@@ -160,6 +160,71 @@ def test_resize_area_matches_opencv(L, k):
         assert np.array_equal(dstf[i], cv2.resize(srcf[i], (size // k, size // k), interpolation=cv2.INTER_AREA))
 
 
+@pytest.mark.parametrize("sh,sw,dh,dw,cn", [(50, 50, 128, 128, 3), (100, 100, 128, 128, 3), (127, 127, 128, 128, 1), (37, 37, 64, 64, 1),
+                                            (3, 3, 10, 10, 3), (20, 31, 45, 77, 3), (255, 255, 301, 301, 3)])
+def test_resize_cubic_matches_opencv(L, oracle, sh, sw, dh, dw, cn):
+    """cubic_u8_kernel against OpenCV's own INTER_CUBIC (oracle.resize_cubic_opencv), bit exact."""
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(sh * 1000 + dw)
+    a = rng.integers(0, 256, (sh, sw, cn), dtype=np.uint8)
+    out = np.empty((dh, dw, cn), np.uint8)
+    assert L.mosaic_kernel_resize_cubic_u8(0, a.ctypes.data, sh, sw, cn, out.ctypes.data, dh, dw) == 0
+    assert np.array_equal(out, oracle.resize_cubic_opencv(a, dh, dw).reshape(dh, dw, cn))
+
+
+def _reference_ingest(oracle, im, size):
+    """ImageLibrary::addImage's image arithmetic (ImageLibrary.cpp:62-83) with the reference's own OpenCV calls."""
+    r, c = im.shape[:2]
+    if c < r:
+        d = (r - c) // 2
+        im = im[d:c + d, :c]
+    elif c > r:
+        d = (c - r) // 2
+        im = im[:r, d:r + d]
+    return oracle.resize_image_exact(np.ascontiguousarray(im), size, size)
+
+
+@pytest.mark.parametrize("rows,cols,size", [(300, 200, 64), (256, 512, 128), (40, 60, 64), (64, 64, 64), (97, 97, 128), (513, 400, 100),
+                                            (31, 90, 32)])
+def test_library_ingest_matches_reference_procedure(L, oracle, rows, cols, size):
+    pytest.importorskip("cv2")
+    rng = np.random.default_rng(rows * 7 + cols)
+    im = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    out = np.empty((size, size, 3), np.uint8)
+    assert L.mosaic_library_ingest(0, im.ctypes.data, rows, cols, im.strides[0], size, out.ctypes.data) == 0
+    assert np.array_equal(out, _reference_ingest(oracle, im, size))
+    # a strided view (row_stride > cols * 3) must give the same result
+    wide = np.zeros((rows, cols + 5, 3), np.uint8)
+    wide[:, :cols] = im
+    out2 = np.empty_like(out)
+    assert L.mosaic_library_ingest(0, wide.ctypes.data, rows, cols, wide.strides[0], size, out2.ctypes.data) == 0
+    assert np.array_equal(out, out2)
+    assert L.mosaic_library_ingest(0, im.ctypes.data, 0, cols, im.strides[0], size, out.ctypes.data) == -1  # empty image
+
+
+def test_image_library_mirror(oracle):
+    """ImageLibrary.addImage / setImageSize (ImageLibrary.cpp:42-86) through the Python mirror."""
+    pytest.importorskip("cv2")
+    from mosaicmagnifique_b200 import ImageLibrary
+    rng = np.random.default_rng(12)
+    lib = ImageLibrary(48, seed=1)
+    srcs = {}
+    for i, (r, c) in enumerate([(100, 80), (48, 48), (30, 45), (200, 200)]):
+        im = rng.integers(0, 256, (r, c, 3), dtype=np.uint8)
+        srcs["im%d" % i] = im
+        idx = lib.addImage(im, "im%d" % i)
+        assert lib.getNames()[idx] == "im%d" % i
+    assert lib.asArray().shape == (4, 48, 48, 3)
+    for name, img in zip(lib.getNames(), lib.getImages()):
+        assert np.array_equal(img, _reference_ingest(oracle, srcs[name], 48))
+    before = {n: im.copy() for n, im in zip(lib.getNames(), lib.getImages())}
+    lib.setImageSize(32)  # resizes the stored (already 48 px) images again, like batchResizeMat on m_originalImages
+    for name, img in zip(lib.getNames(), lib.getImages()):
+        assert np.array_equal(img, oracle.resize_image_exact(before[name], 32, 32))
+    with pytest.raises(ValueError):
+        lib.addImage(np.zeros((0, 5, 3), np.uint8))
+
+
 def test_microbench_runs(L):
     out = np.zeros(8, np.float64)
     assert L.mosaic_kernel_microbench(0, out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 8) == 0
