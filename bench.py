@@ -35,8 +35,9 @@ WORK = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1}, 1: {"flop": 9, "s
 EXECUTED = {2: {"mufu": 9, "fp32_lane_ops": 81}, 0: {"mufu": 1, "fp32_lane_ops": 7}, 1: {"mufu": 1, "fp32_lane_ops": 7}}
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the difference kernel, per launch on 1 GPU, from the ncu captures committed
-# under profiles/ (r1_dram_traffic_*_final.csv; final code of round 1). Not measurable inside an un-profiled run.
-NCU_TRAFFIC_BYTES = {"cfg4": 124474822144 + 205453312, "cfg5": 35904559360 + 13339392}
+# under profiles/ (cfg4: r1_diff_sum_ciede2000_v4_cfg4.txt, the shipped kernel; cfg5: r1_dram_traffic_cfg5_final.csv).
+# Not measurable inside an un-profiled run.
+NCU_TRAFFIC_BYTES = {"cfg4": 132214958000 + 197510656, "cfg5": 35904559360 + 13339392}
 
 WORKLOADS = {
     # name: (H, W, n_lib, cell, detail, diff, range, addition, seed)
@@ -346,7 +347,7 @@ def main():
         "bound": "mufu", "kernel": "diff_sum_kernel",
         "achieved": sfu_rate / 1e9, "peak": mb[2] / 1e9, "unit": "Gop/s", "frac": sfu_rate / mb[2],
         "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
-        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_dram_traffic_*_final.csv)",
+        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_diff_sum_ciede2000_v4_cfg4.txt, r1_dram_traffic_cfg5_final.csv)",
         "note": "SURVEY 8d counts the REFERENCE formula: %d flop + %d special-function ops per pixel-diff; peak = MUFU.RSQ rate "
                 "measured live by the in-library micro-benchmark (16 lanes/clk/SM). The kernel's trig-free CIEDE2000 executes only "
                 "%d MUFU ops and %d FP32 lane-ops per pixel-diff, which is why frac can exceed 1; see executed_* (pipe utilisation "
