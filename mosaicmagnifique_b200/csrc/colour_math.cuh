@@ -148,15 +148,15 @@ MM_HD mm_f2 v_max(mm_f2 a, mm_f2 b) { return mm_f2{fmaxf(a.x, b.x), fmaxf(a.y, b
 //     (sl25 = 25 S_L multiplies both), the constants of S_C and T, and the result's overall 1/25 (plus the 1/2 of the
 //     half-scale deltas) into the per-pixel weight: w = MM_CIEDE_WEIGHT for an active pixel.
 //
-// Work per pixel pair: 9 MUFU + 81 FP32 lane-ops (reference: 27 special-function ops + ~110 flop in f64). Besides the
+// Work per pixel pair: 9 MUFU + 80 FP32 lane-ops (reference: 27 special-function ops + ~110 flop in f64). Besides the
 // algebra described at the top of this file:
 //   * T = P4(cos h) + sin h * Q3(cos h): the four cosines of T are Chebyshev polynomials of cos h and sin h times
 //     Chebyshev-U, collected into one quartic and one cubic (8 FMA instead of recurrences);
 //   * mean hue = hue(v1) + dh/2: e^(i dh/2) is (P + dot, cross) for dot > 0 and (|cross|, +-(P - dot)) otherwise
 //     (both well conditioned), rotated by v1 and normalised once;
-//   * dTheta needs only (hbar - 275deg)^2: a quartic in v = 1 - cos(hbar - 275deg) (|error| of the Gaussian < 7e-8,
-//     for |hbar - 275deg| >= 90deg the Gaussian is < 2.4e-6 whatever the polynomial gives); sin(2 dTheta) is an odd
-//     polynomial (1.6e-8);
+//   * dTheta needs only (hbar - 275deg)^2: v times a Gaussian-weighted cubic in v = 1 - cos(hbar - 275deg) (|error| of
+//     R_T < 1.1e-6; for |hbar - 275deg| >= 90deg the Gaussian is < 2.4e-6 whatever the polynomial gives); sin(2 dTheta)
+//     is an odd polynomial (1.6e-8);
 //   * S_L = 1 + 0.015 q rsq(20 + q) as two nested FMAs around the rsq;
 //   * the three divisions AND the final square root are one rsq: dE = sqrt(N)/den = N rsq(N den^2) over the common
 //     denominator den = S_L S_C S_H;
@@ -236,11 +236,12 @@ MM_HD V mm_ciede2000_stored_v(float L1, float a1, float b1, float C1, V L2, V a2
     // the Gaussian is < 2^-18.7 = 2.4e-6 there whatever it evaluates to (the true value is smaller still): no clamp
     const V v = v_fma(K(0.99619469809f), sh, v_fma(K(-0.08715574275f), ch, K(1.0f)));
     const float kE = -1.44269504089f / (0.43633231299f * 0.43633231299f);
-    V pe = K(kE * 0.017463532422f);
-    pe = v_fma(pe, v, K(kE * 0.025150421036f));
-    pe = v_fma(pe, v, K(kE * 0.089459953974f));
-    pe = v_fma(pe, v, K(kE * 0.333304633506f));
-    pe = v_fma(pe, v, K(kE * 2.0f));
+    // (hbar - 275deg)^2 / v as a cubic in v, fitted with the Gaussian as weight: what matters is the error of R_T, and
+    // that is < 1.1e-6 of its range (+-1.73) over the whole circle (the unweighted quartic it replaces gave 1.3e-7)
+    V pe = K(kE * 0.04221360751201737f);
+    pe = v_fma(pe, v, K(kE * 0.08423404788568702f));
+    pe = v_fma(pe, v, K(kE * 0.3338742216190624f));
+    pe = v_fma(pe, v, K(kE * 1.9999825857294062f));
     const V gauss = v_ex2(v_mul(pe, v));
     // -2 sin(2 dTheta), 2 dTheta = 60deg * gauss: odd polynomial in gauss (|err| < 1.6e-8); sign and the 2 of R_C folded
     const V g2 = v_mul(gauss, gauss);

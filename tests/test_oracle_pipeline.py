@@ -61,3 +61,39 @@ def test_grid_state_splits_by_entropy(oracle):
     assert [s.shape for s in st] == [(6, 8), (10, 14), (18, 26)]
     n = [(s >= 0).sum() for s in st]
     assert n[0] > 0 and n[1] > 0 and n[2] > 0
+
+
+# ---------------------------------------------------------------- committed generator-level golden vectors
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generator_golden.npz"))
+
+
+def golden_case(oracle, G, name):
+    """Rebuilds the oracle-side inputs of one fixture of tests/golden/generator_golden.npz (made by make_generator_golden.py)."""
+    shape = oracle.CellShape.from_mask(G[name + "/mask"])
+    fields = ("row_spacing", "col_spacing", "alt_row_spacing", "alt_col_spacing", "alt_row_offset", "alt_col_offset",
+              "alt_col_flip_h", "alt_col_flip_v", "alt_row_flip_h", "alt_row_flip_v")
+    for f, v in zip(fields, G[name + "/shape"]):
+        setattr(shape, f, bool(v) if "flip" in f else int(v))
+    diff, detail, steps, rr, ra, scheme = (int(v) for v in G[name + "/params"])
+    return shape, diff, detail, steps, rr, ra, scheme
+
+
+def test_oracle_reproduces_generator_golden(oracle):
+    """The oracle must reproduce its own committed outputs bit for bit (grid states and grids) and to 1e-12 (f64 sums):
+    a different cv2 / numpy / compiler on the machine that runs the tests cannot silently move the parity target."""
+    pytest.importorskip("cv2")
+    G = _golden()
+    for name in G["names"]:
+        name = str(name)
+        shape, diff, detail, steps, rr, ra, scheme = golden_case(oracle, G, name)
+        group = oracle.CellGroup.make(shape, detail, steps)
+        states = oracle.grid_state(group, G[name + "/main"])
+        res = oracle.generate(G[name + "/main"], G[name + "/lib"], group, states, diff, scheme, rr, ra, want_D=True)
+        assert len(states) == steps + 1
+        for s, (st, r) in enumerate(zip(states, res)):
+            assert np.array_equal(st, G["%s/state%d" % (name, s)])
+            assert np.array_equal(r.grid, G["%s/grid%d" % (name, s)])
+            np.testing.assert_allclose(r.D, G["%s/D%d" % (name, s)], rtol=1e-12, atol=0)
