@@ -175,8 +175,8 @@ int mosaic_kernel_resize_cubic_u8(int device, const uint8_t *src, int src_h, int
 int mosaic_library_ingest(int device, const uint8_t *bgr, int rows, int cols, size_t row_stride, int image_size, uint8_t *out);
 /* FP32 / MUFU pipe-rate micro-benchmark (roofline denominators): out[0] FFMA lane-ops/s, [1] FFMA2 lane-ops/s,
  * [2] MUFU.RSQ ops/s, [3] MUFU.EX2 ops/s, [4] SM count, [5] cycles per 16-FFMA loop iteration, and (n_out >= 9) the rate of a
- * synthetic loop in the CIEDE2000 kernel's instruction proportions, in "pixel pairs"/s: [6] 42 FFMA2 + 10 MUFU + 10 ALU,
- * [7] 42 FFMA2 + 10 MUFU, [8] 42 FFMA2 */
+ * synthetic loop in the CIEDE2000 kernel's instruction proportions, in "pixel pairs"/s: [6] 40 FFMA2 + 9 MUFU + 5 ALU,
+ * [7] 40 FFMA2 + 9 MUFU, [8] 40 FFMA2 */
 int mosaic_kernel_microbench(int device, double *out, int n_out);
 
 /* ---- host-side geometry (no GPU needed): GridUtility.cpp:25-52, 86-132; CellShape::resized */

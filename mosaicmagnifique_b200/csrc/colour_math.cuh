@@ -148,7 +148,7 @@ MM_HD mm_f2 v_max(mm_f2 a, mm_f2 b) { return mm_f2{fmaxf(a.x, b.x), fmaxf(a.y, b
 //     (sl25 = 25 S_L multiplies both), the constants of S_C and T, and the result's overall 1/25 (plus the 1/2 of the
 //     half-scale deltas) into the per-pixel weight: w = MM_CIEDE_WEIGHT for an active pixel.
 //
-// Work per pixel pair: 9 MUFU + 80 FP32 lane-ops (reference: 27 special-function ops + ~110 flop in f64). Besides the
+// Work per pixel pair: 9 MUFU + 79 FP32 lane-ops + 5 ALU ops (reference: 27 special-function ops + ~110 flop in f64). Besides the
 // algebra described at the top of this file:
 //   * T = P4(cos h) + sin h * Q3(cos h): the four cosines of T are Chebyshev polynomials of cos h and sin h times
 //     Chebyshev-U, collected into one quartic and one cubic (8 FMA instead of recurrences);

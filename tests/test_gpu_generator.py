@@ -289,3 +289,85 @@ def _downstream_allowance(ties):
     # a tie-band cell that picks the other candidate changes the repeat counts of the cells after it, which may then
     # legitimately choose differently from the recorded grid (check_grid above is the teacher-forced criterion)
     return 0 if ties == 0 else 10 ** 9
+
+
+# ---------------------------------------------------------------- ragged / degenerate inputs
+
+@pytest.mark.parametrize("n_lib", [1, 3, 13])
+def test_tiny_and_ragged_libraries(oracle, n_lib):
+    """Library sizes below / not a multiple of the kernel's library tile (8 images), more repeats than images."""
+    main, lib = _inputs(71 + n_lib, 130, 170, n_lib, 32)
+    _run_case(oracle, main, lib, oracle.CellShape.square(32), 2, 100, 0, 2, 700)
+    _run_case(oracle, main, lib, oracle.CellShape.square(32), 0, 50, 0, 1, 50)
+
+
+def test_main_image_smaller_than_a_cell(oracle):
+    """Every cell is an edge cell (clipped on all sides by the padded grid, GridUtility::PAD_GRID)."""
+    main, lib = _inputs(81, 20, 27, 10, 32)
+    total, _ = _run_case(oracle, main, lib, oracle.CellShape.square(32), 2, 100, 0, 1, 10)
+    assert total >= 1
+
+
+def test_repeat_range_larger_than_grid(oracle):
+    main, lib = _inputs(82, 100, 140, 20, 32)
+    _run_case(oracle, main, lib, oracle.CellShape.square(32), 1, 100, 0, 50, 100000)
+
+
+def test_detail_one_pixel(oracle):
+    """detail 3 % of a 32 px cell = max(int(0.96), 1) = 1 pixel per cell (CellGroup.cpp:114)."""
+    main, lib = _inputs(83, 100, 140, 20, 32)
+    _run_case(oracle, main, lib, oracle.CellShape.square(32), 0, 3, 0, 2, 10)
+
+
+def test_identical_library_images_lowest_index_wins(oracle):
+    """Exact ties: the CPU's strict < keeps the lowest index (CPUPhotomosaicGenerator.cpp:163-168)."""
+    from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator
+    main, lib = _inputs(84, 96, 128, 6, 32)
+    lib = np.concatenate([lib, lib, lib])  # images i, i + 6, i + 12 are identical
+    for diff in (0, 2):
+        gen = PhotomosaicGenerator(0)
+        gen.setMainImage(main)
+        gen.setLibrary(lib)
+        gen.setColourDifference(diff)
+        cg = CellGroup()
+        cg.setCellShape(CellShape(32))
+        gen.setCellGroup(cg)
+        gen.computeGridState()
+        for rr, ra in ((0, 0), (2, 0)):  # fused argmin epilogue, and the selection kernels with a zero penalty
+            gen.setRepeat(rr, ra)
+            assert gen.generateBestFits()
+            g = gen.getBestFits()[0]
+            assert (g[g >= 0] < 6).all()
+        gen.close()
+
+
+def test_all_cells_invalid_and_single_valid_cell(oracle):
+    """A grid state with no valid cell gives back the same grid (the reference's loops run zero times,
+    CPUPhotomosaicGenerator.cpp:64-104); one valid cell alone is filled."""
+    from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator
+    main, lib = _inputs(85, 96, 128, 9, 32)
+    gen = PhotomosaicGenerator(0)
+    gen.setMainImage(main)
+    gen.setLibrary(lib)
+    gen.setColourDifference(2)
+    cg = CellGroup()
+    cg.setCellShape(CellShape(32))
+    gen.setCellGroup(cg)
+    state = gen.computeGridState()
+    empty = [np.full_like(state[0], -1)]
+    gen.setGridState(empty)
+    gen.setRepeat(2, 100)
+    assert gen.generateBestFits()
+    assert (gen.getBestFits()[0] == -1).all()
+    one = [np.full_like(state[0], -1)]
+    one[0][3, 3] = 0
+    gen.setGridState(one)
+    gen.setKeepDifferences(True)
+    assert gen.generateBestFits()
+    g = gen.getBestFits()[0]
+    assert (g >= 0).sum() == 1 and g[3, 3] >= 0
+    og = oracle.CellGroup.make(oracle.CellShape.square(32), 100, 0)
+    want = oracle.generate(main, lib, og, one, 2, 0, 2, 100, want_D=True)[0]
+    assert g[3, 3] == want.grid[3, 3]
+    assert rel_err(gen.getDifferences(0), want.D).max() < TOL
+    gen.close()
