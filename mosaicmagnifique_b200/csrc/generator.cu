@@ -469,6 +469,8 @@ void run_pipeline(G *g, bool candidates_only)
     // ---- Preprocess: library -> working space at the detail size of step 0 (:255-290)
     DevBuf &d_lib_work = g->ws.lib_work, &d_lib_small = g->ws.lib_small;
     int lib_ds = g->lib_size;
+    const uint8_t *lib_u8_at_ds = nullptr;
+    bool fuse_lib_conversion = false;
     {
         const uint8_t *src = g->d_lib_u8.as<uint8_t>();
         if (g->group.detail != 1.0) {
@@ -483,11 +485,17 @@ void run_pipeline(G *g, bool candidates_only)
             tm.kernel_launches++;
             src = d_lib_small.as<uint8_t>();
         }
-        d_lib_work.alloc((size_t)N * lib_ds * lib_ds * 3 * sizeof(float), st);
-        // the library is one tall image of N * ds rows
-        CU(launch_to_working_space(src, (size_t)lib_ds * 3, (int)std::min<int64_t>(N * lib_ds, INT32_MAX), lib_ds,
-                                   d_lib_work.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
-        tm.kernel_launches++;
+        // CIEDE2000 with a single size step: the Lab conversion is fused into the tile-packing kernel below (straight from
+        // the 8U library), the f32 working-space copy is only materialised when a later step has to halve it
+        lib_u8_at_ds = src;
+        fuse_lib_conversion = layout == kLayoutCiede && n_steps == 1;
+        if (!fuse_lib_conversion) {
+            d_lib_work.alloc((size_t)N * lib_ds * lib_ds * 3 * sizeof(float), st);
+            // the library is one tall image of N * ds rows
+            CU(launch_to_working_space(src, (size_t)lib_ds * 3, (int)std::min<int64_t>(N * lib_ds, INT32_MAX), lib_ds,
+                                       d_lib_work.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
+            tm.kernel_launches++;
+        }
     }
     clock.end();
 
@@ -547,8 +555,12 @@ void run_pipeline(G *g, bool candidates_only)
 
         // library tiles
         d.lib_packed.alloc((size_t)n_lib_tiles * p.n_chunks * tg.lib_block, st);
-        CU(launch_pack_library(d_lib_work.as<float>(), d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
-                               n_lib_tiles, layout, st));
+        if (fuse_lib_conversion)
+            CU(launch_pack_library_ciede(lib_u8_at_ds, true, d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
+                                         n_lib_tiles, g->d_lut.as<int16_t>(), st));
+        else
+            CU(launch_pack_library(d_lib_work.as<float>(), d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
+                                   n_lib_tiles, layout, st));
         tm.kernel_launches++;
 
         // cell descriptors of this rank's cells (getCellAt, PhotomosaicGeneratorBase.cpp:293-329)

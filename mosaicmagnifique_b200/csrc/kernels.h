@@ -103,6 +103,11 @@ cudaError_t launch_cubic_u8(const uint8_t *src, int sh, int sw, int cn, uint8_t 
 cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
                                 int n_chunks, int n_lib_tiles, PackLayout layout, cudaStream_t stream);
 
+// CIEDE2000 layout straight from the 8U BGR library at the detail size (Lab conversion fused, no f32 intermediate) or from
+// the f32 working-space library; padding slots are written by the same pass
+cudaError_t launch_pack_library_ciede(const void *src, bool src_is_u8, void *packed, int64_t n, int P, const int *pix_list,
+                                      int n_active, int n_chunks, int n_lib_tiles, const int16_t *lab_lut, cudaStream_t stream);
+
 struct CellDesc {
     int x0, y0;          // top-left of the (unclipped) cell rect in main-image space
     int bx, by, bw, bh;  // detail-space bound

@@ -360,56 +360,99 @@ __device__ __forceinline__ float4 half_scale_lab(float L, float a, float b)
     return make_float4(fmaf(0.5f, L, -25.0f), MM_CIEDE_AB_SCALE * a, MM_CIEDE_AB_SCALE * b, MM_CIEDE_AB_SCALE * chroma_of(a, b));
 }
 
-__global__ void pack_library_kernel(const float *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
-                                    const int *__restrict__ pix_list, int n_active, int n_chunks, int layout)
+// Euclidean layout (diff_euclid.cu): pixel-major, NEGATED: [lib_tile][chunk][pixel][x0,x1,x2][64 images]; one thread per
+// (image, active pixel), padding comes from the memset in launch_pack_library
+__global__ void pack_library_euclid_kernel(const float *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
+                                           const int *__restrict__ pix_list, int n_active, int n_chunks)
 {
-    const bool with_chroma = layout == kLayoutCiede;
-    // one thread per (image, active pixel)
     const size_t total = (size_t)n * n_active;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int q = (int)(i % n_active);
         const size_t im = i / n_active;
         const float *s = lib + (im * P + pix_list[q]) * 3;
-        float4 v = make_float4(s[0], s[1], s[2], 0.0f);
-        if (with_chroma)
-            v = half_scale_lab(v.x, v.y, v.z);
-        if (layout == kLayoutEuclid) {
-            // pixel-major, NEGATED: [lib_tile][chunk][pixel][x0,x1,x2][64 images] (diff_euclid.cu)
-            const size_t tile = im / MM_ETN, ti = im % MM_ETN;
-            const int chunk = q / MM_EKP, pi = q % MM_EKP;
-            float *f = reinterpret_cast<float *>(packed + (tile * n_chunks + chunk) * (size_t)(MM_EKP * 3 * MM_ETN * 4));
-            f[(pi * 3 + 0) * MM_ETN + ti] = -v.x;
-            f[(pi * 3 + 1) * MM_ETN + ti] = -v.y;
-            f[(pi * 3 + 2) * MM_ETN + ti] = -v.z;
-            continue;
-        }
-        const size_t tile = im / MM_TNB, ti = im % MM_TNB;
-        const int chunk = q / MM_KP, pi = q % MM_KP;
-        unsigned char *blk = packed + (tile * n_chunks + chunk) * (size_t)(MM_TNB * MM_KP * 16);
-        if (with_chroma) {
-            // image pairs interleaved for the packed-FP32 kernel: [pair][0][p] = (L0, L1, a0, a1), [pair][1][p] = (b0, b1, C0, C1)
-            float *f = reinterpret_cast<float *>(blk) + ((ti >> 1) * 2 * MM_KP + pi) * 4 + (ti & 1);
-            f[0] = v.x;
-            f[2] = v.y;
-            f[MM_KP * 4 + 0] = v.z;
-            f[MM_KP * 4 + 2] = v.w;
-        } else {
-            reinterpret_cast<float4 *>(blk)[ti * MM_KP + pi] = v;
-        }
+        const size_t tile = im / MM_ETN, ti = im % MM_ETN;
+        const int chunk = q / MM_EKP, pi = q % MM_EKP;
+        float *f = reinterpret_cast<float *>(packed + (tile * n_chunks + chunk) * (size_t)(MM_EKP * 3 * MM_ETN * 4));
+        f[(pi * 3 + 0) * MM_ETN + ti] = -s[0];
+        f[(pi * 3 + 1) * MM_ETN + ti] = -s[1];
+        f[(pi * 3 + 2) * MM_ETN + ti] = -s[2];
     }
+}
+
+// CIEDE2000 layout, one thread per (image PAIR slot, pixel slot) of the padded tile grid: two complete float4 stores per
+// thread (consecutive threads = consecutive pixels -> fully coalesced), padding slots written as zeros by the same pass
+// (no separate memset of the 2.6 GB tensor). kFromU8: the source is the 8U BGR library at the detail size and the Lab
+// conversion (lab_from_bgr8, same arithmetic as to_working_space_kernel) is fused in -- the f32 working-space copy of the
+// library (1.97 GB written and read again at config 4) is never materialised. Used when there is a single size step;
+// with size steps the f32 copy is needed for the per-step halving (CPUPhotomosaicGenerator.cpp:95-99).
+template <bool kFromU8>
+__global__ void pack_library_ciede_kernel(const void *__restrict__ src, unsigned char *__restrict__ packed, int64_t n, int P,
+                                          const int *__restrict__ pix_list, int n_active, int n_chunks, int64_t n_pair_slots,
+                                          const int16_t *__restrict__ lut)
+{
+    const int slots_per_image = n_chunks * MM_KP;
+    const size_t total = (size_t)n_pair_slots * slots_per_image;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int q = (int)(i % slots_per_image);
+        const int64_t pr = (int64_t)(i / slots_per_image);
+        float4 v[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        if (q < n_active) {
+            const int px = pix_list[q];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int64_t im = pr * 2 + j;
+                if (im >= n)
+                    continue;
+                float L, a, b;
+                if (kFromU8) {
+                    const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src) + ((size_t)im * P + px) * 3;
+                    lab_from_bgr8(s8[0], s8[1], s8[2], lut, L, a, b);
+                } else {
+                    const float *sf = reinterpret_cast<const float *>(src) + ((size_t)im * P + px) * 3;
+                    L = sf[0];
+                    a = sf[1];
+                    b = sf[2];
+                }
+                v[j] = half_scale_lab(L, a, b);
+            }
+        }
+        const int64_t tile = pr / (MM_TNB / 2);
+        const int tp = (int)(pr % (MM_TNB / 2)), chunk = q / MM_KP, pi = q % MM_KP;
+        float4 *blk = reinterpret_cast<float4 *>(packed + ((size_t)tile * n_chunks + chunk) * (size_t)(MM_TNB * MM_KP * 16));
+        // [pair][0][p] = (L0, L1, a0, a1), [pair][1][p] = (b0, b1, C0, C1)
+        blk[(tp * 2 + 0) * MM_KP + pi] = make_float4(v[0].x, v[1].x, v[0].y, v[1].y);
+        blk[(tp * 2 + 1) * MM_KP + pi] = make_float4(v[0].z, v[1].z, v[0].w, v[1].w);
+    }
+}
+
+cudaError_t launch_pack_library_ciede(const void *src, bool src_is_u8, void *packed, int64_t n, int P, const int *pix_list,
+                                      int n_active, int n_chunks, int n_lib_tiles, const int16_t *lab_lut, cudaStream_t stream)
+{
+    const int64_t n_pair_slots = (int64_t)n_lib_tiles * (MM_TNB / 2);
+    const size_t total = (size_t)n_pair_slots * n_chunks * MM_KP;
+    if (total == 0)
+        return cudaSuccess;
+    if (src_is_u8)
+        pack_library_ciede_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(src, (unsigned char *)packed, n, P, pix_list, n_active,
+                                                                                  n_chunks, n_pair_slots, lab_lut);
+    else
+        pack_library_ciede_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(src, (unsigned char *)packed, n, P, pix_list, n_active,
+                                                                                   n_chunks, n_pair_slots, lab_lut);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P, const int *pix_list, int n_active,
                                 int n_chunks, int n_lib_tiles, PackLayout layout, cudaStream_t stream)
 {
+    if (layout == kLayoutCiede)
+        return launch_pack_library_ciede(lib, false, packed, n, P, pix_list, n_active, n_chunks, n_lib_tiles, nullptr, stream);
     cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_lib_tiles * n_chunks * tile_geom(layout).lib_block, stream);
     if (e != cudaSuccess)
         return e;
     const size_t total = (size_t)n * n_active;
     if (total == 0)
         return cudaSuccess;
-    pack_library_kernel<<<grid_for(total, 256), 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active,
-                                                                  n_chunks, (int)layout);
+    pack_library_euclid_kernel<<<grid_for(total, 256), 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active, n_chunks);
     return cudaGetLastError();
 }
 
