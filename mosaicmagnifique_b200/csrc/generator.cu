@@ -425,8 +425,10 @@ void run_pipeline(G *g, bool candidates_only)
     enum { kPre = 0, kDiff = 1, kSel = 2 };
 
     if (!g->d_lut.p) {
-        g->d_lut.alloc(33 * 33 * 33 * 3 * sizeof(int16_t), st);
-        CU(cudaMemcpyAsync(g->d_lut.p, mm_lab_lut_s16, g->d_lut.bytes, cudaMemcpyHostToDevice, st));
+        const std::vector<int16_t> lut4 = expand_lab_lut(mm_lab_lut_s16);
+        g->d_lut.alloc(lut4.size() * sizeof(int16_t), st);
+        CU(cudaMemcpyAsync(g->d_lut.p, lut4.data(), g->d_lut.bytes, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));  // lut4 is a local
         tm.h2d_bytes += (double)g->d_lut.bytes;
     }
 
@@ -461,7 +463,7 @@ void run_pipeline(G *g, bool candidates_only)
             src = g->ws.main_var_u8.as<uint8_t>() + row_off_px * 3;
         }
         CU(launch_to_working_space(src, (size_t)g->img_cols * 3, n_rows_conv, g->img_cols,
-                                   d_main_f32.as<float>() + ((size_t)v * n_main_px + row_off_px) * 3, is_lab, g->d_lut.as<int16_t>(),
+                                   d_main_f32.as<float>() + ((size_t)v * n_main_px + row_off_px) * 3, is_lab, g->d_lut.as<short4>(),
                                    nullptr, st));
         tm.kernel_launches++;
     }
@@ -493,7 +495,7 @@ void run_pipeline(G *g, bool candidates_only)
             d_lib_work.alloc((size_t)N * lib_ds * lib_ds * 3 * sizeof(float), st);
             // the library is one tall image of N * ds rows
             CU(launch_to_working_space(src, (size_t)lib_ds * 3, (int)std::min<int64_t>(N * lib_ds, INT32_MAX), lib_ds,
-                                       d_lib_work.as<float>(), is_lab, g->d_lut.as<int16_t>(), nullptr, st));
+                                       d_lib_work.as<float>(), is_lab, g->d_lut.as<short4>(), nullptr, st));
             tm.kernel_launches++;
         }
     }
@@ -557,7 +559,7 @@ void run_pipeline(G *g, bool candidates_only)
         d.lib_packed.alloc((size_t)n_lib_tiles * p.n_chunks * tg.lib_block, st);
         if (fuse_lib_conversion)
             CU(launch_pack_library_ciede(lib_u8_at_ds, true, d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
-                                         n_lib_tiles, g->d_lut.as<int16_t>(), st));
+                                         n_lib_tiles, g->d_lut.as<short4>(), st));
         else
             CU(launch_pack_library(d_lib_work.as<float>(), d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
                                    n_lib_tiles, layout, st));

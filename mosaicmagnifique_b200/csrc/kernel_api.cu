@@ -226,10 +226,11 @@ int mosaic_kernel_bgr_to_lab(int device, const uint8_t *bgr, int64_t n_pixels, f
     Dev d_in, d_out, d_lut;
     KCHECK(d_in.alloc((size_t)n_pixels * 3));
     KCHECK(d_out.alloc((size_t)n_pixels * 3 * sizeof(float)));
-    KCHECK(d_lut.alloc(33 * 33 * 33 * 3 * sizeof(int16_t)));
+    const std::vector<int16_t> lut4 = expand_lab_lut(mm_lab_lut_s16);
+    KCHECK(d_lut.alloc(lut4.size() * sizeof(int16_t)));
     KCHECK(cudaMemcpy(d_in.p, bgr, (size_t)n_pixels * 3, cudaMemcpyHostToDevice));
-    KCHECK(cudaMemcpy(d_lut.p, mm_lab_lut_s16, 33 * 33 * 33 * 3 * sizeof(int16_t), cudaMemcpyHostToDevice));
-    KCHECK(launch_to_working_space(d_in.as<uint8_t>(), (size_t)n_pixels * 3, 1, (int)n_pixels, d_out.as<float>(), true, d_lut.as<int16_t>(),
+    KCHECK(cudaMemcpy(d_lut.p, lut4.data(), lut4.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    KCHECK(launch_to_working_space(d_in.as<uint8_t>(), (size_t)n_pixels * 3, 1, (int)n_pixels, d_out.as<float>(), true, d_lut.as<short4>(),
                                    nullptr, 0));
     KCHECK(cudaMemcpy(lab_out, d_out.p, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyDeviceToHost));
     return MOSAIC_OK;

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 // colour difference types (values of the reference enum, src/Photomosaic/ColourDifference.h:13-19)
 #define MM_DIFF_RGB_EUCLIDEAN 0
 #define MM_DIFF_CIE76 1
@@ -74,8 +76,19 @@ cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, f
 
 // ---- prep_kernels.cu
 // u8 BGR -> working space f32 AoS [pixel][3]: Lab through the OpenCV-compatible LUT (is_lab) or a plain cast.
+// lab_lut: the 33^3 OpenCV-compatible table expanded to 8-byte entries (L, a, b, 0) by expand_lab_lut
 cudaError_t launch_to_working_space(const uint8_t *bgr, size_t row_stride, int rows, int cols, float *out, bool is_lab,
-                                    const int16_t *lab_lut, const int *c8, cudaStream_t stream);
+                                    const short4 *lab_lut, const int *c8, cudaStream_t stream);
+constexpr size_t kLabLutEntries = 33 * 33 * 33;
+// 3 x int16 per entry (lab_lut.S, data/lab_lut_s16.bin) -> 4 x int16 per entry, so that a cube corner is one 8-byte load
+inline std::vector<int16_t> expand_lab_lut(const int16_t *lut3)
+{
+    std::vector<int16_t> out(kLabLutEntries * 4, 0);
+    for (size_t i = 0; i < kLabLutEntries; ++i)
+        for (int c = 0; c < 3; ++c)
+            out[i * 4 + c] = lut3[i * 3 + c];
+    return out;
+}
 // hue-rotated 8U copy of an 8U BGR image (ColourScheme.cpp:36-177, OpenCV float HSV_FULL round trip)
 cudaError_t launch_hue_rotate(const uint8_t *in, uint8_t *out, int rows, int cols, float rot, cudaStream_t stream);
 // INTER_AREA for integer ratios, 8U 3-channel, batch of n square images (src size s -> dst size s / k)
@@ -106,7 +119,7 @@ cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P
 // CIEDE2000 layout straight from the 8U BGR library at the detail size (Lab conversion fused, no f32 intermediate) or from
 // the f32 working-space library; padding slots are written by the same pass
 cudaError_t launch_pack_library_ciede(const void *src, bool src_is_u8, void *packed, int64_t n, int P, const int *pix_list,
-                                      int n_active, int n_chunks, int n_lib_tiles, const int16_t *lab_lut, cudaStream_t stream);
+                                      int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream);
 
 struct CellDesc {
     int x0, y0;          // top-left of the (unclipped) cell rect in main-image space

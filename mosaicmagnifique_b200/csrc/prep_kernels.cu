@@ -28,7 +28,7 @@ __device__ __forceinline__ int lab_coord(unsigned char v)
 }
 
 __device__ __forceinline__ void lab_from_bgr8(unsigned char b8, unsigned char g8, unsigned char r8,
-                                              const int16_t *__restrict__ lut, float &L, float &a, float &b)
+                                              const short4 *__restrict__ lut, float &L, float &a, float &b)
 {
     const int cb = lab_coord(b8), cg = lab_coord(g8), cr = lab_coord(r8);
     const int tb = cb >> 9, tg = cg >> 9, tr = cr >> 9;
@@ -42,10 +42,10 @@ __device__ __forceinline__ void lab_from_bgr8(unsigned char b8, unsigned char g8
             for (int dr = 0; dr < 2; ++dr) {
                 const int w = (db ? wb : 16 - wb) * (dg ? wg : 16 - wg) * (dr ? wr : 16 - wr);
                 const int ib = min(tb + db, 32), ig = min(tg + dg, 32), ir = min(tr + dr, 32);
-                const int16_t *e = lut + ((ib * 33 + ig) * 33 + ir) * 3;
-                sL += w * e[0];
-                sa += w * e[1];
-                sb += w * e[2];
+                const short4 e = lut[(ib * 33 + ig) * 33 + ir];  // (L, a, b, -): one 8-byte load per cube corner
+                sL += w * e.x;
+                sa += w * e.y;
+                sb += w * e.z;
             }
     const int iL = (sL + 2048) >> 12, ia = (sa + 2048) >> 12, ib2 = (sb + 2048) >> 12;
     L = __fmul_rn((float)iL * (1.0f / 16384.0f), 100.0f);
@@ -54,7 +54,7 @@ __device__ __forceinline__ void lab_from_bgr8(unsigned char b8, unsigned char g8
 }
 
 __global__ void to_working_space_kernel(const uint8_t *__restrict__ bgr, size_t row_stride, int rows, int cols,
-                                        float *__restrict__ out, bool is_lab, const int16_t *__restrict__ lut)
+                                        float *__restrict__ out, bool is_lab, const short4 *__restrict__ lut)
 {
     const size_t n = (size_t)rows * cols;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -82,7 +82,7 @@ static int grid_for(size_t n, int block)
 }
 
 cudaError_t launch_to_working_space(const uint8_t *bgr, size_t row_stride, int rows, int cols, float *out, bool is_lab,
-                                    const int16_t *lab_lut, const int *, cudaStream_t stream)
+                                    const short4 *lab_lut, const int *, cudaStream_t stream)
 {
     const size_t n = (size_t)rows * cols;
     if (n == 0)
@@ -388,7 +388,7 @@ __global__ void pack_library_euclid_kernel(const float *__restrict__ lib, unsign
 template <bool kFromU8>
 __global__ void pack_library_ciede_kernel(const void *__restrict__ src, unsigned char *__restrict__ packed, int64_t n, int P,
                                           const int *__restrict__ pix_list, int n_active, int n_chunks, int64_t n_pair_slots,
-                                          const int16_t *__restrict__ lut)
+                                          const short4 *__restrict__ lut)
 {
     const int slots_per_image = n_chunks * MM_KP;
     const size_t total = (size_t)n_pair_slots * slots_per_image;
@@ -426,7 +426,7 @@ __global__ void pack_library_ciede_kernel(const void *__restrict__ src, unsigned
 }
 
 cudaError_t launch_pack_library_ciede(const void *src, bool src_is_u8, void *packed, int64_t n, int P, const int *pix_list,
-                                      int n_active, int n_chunks, int n_lib_tiles, const int16_t *lab_lut, cudaStream_t stream)
+                                      int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream)
 {
     const int64_t n_pair_slots = (int64_t)n_lib_tiles * (MM_TNB / 2);
     const size_t total = (size_t)n_pair_slots * n_chunks * MM_KP;
