@@ -189,6 +189,9 @@ int mosaic_flip_at(const mosaic_cell_shape *shape, int x, int y); /* flip_h + 2 
 int mosaic_host_grid_state(const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size, int detail_percent, int size_steps,
                            const uint8_t *bgr, int rows, int cols, size_t row_stride, int max_steps, int *n_steps, int *step_rows,
                            int *step_cols, int64_t *out, size_t out_capacity);
+/* GridBounds::addBound x n + mergeBounds (Grid/GridBounds.cpp:26-104): rects are x, y, w, h quadruples; returns the number of
+ * merged bounds (the first min(count, out_capacity) are written to out), or a negative status */
+int mosaic_host_merge_bounds(const int *rects_xywh, int n, int *out_xywh, int out_capacity);
 /* cv::resize(INTER_AREA) for 8U images with cn channels (OpenCV-compatible, any down-scaling ratio) */
 int mosaic_host_resize_area_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w);
 /* cv::resize(INTER_CUBIC) for 8U images with cn channels, as OpenCV's own (non-IPP) code computes it: what

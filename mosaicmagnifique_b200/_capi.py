@@ -94,6 +94,7 @@ def capi():
         "mosaic_rect_at": (None, [shp, i, i, ip]),
         "mosaic_flip_at": (i, [shp, i, i]),
         "mosaic_host_grid_state": (i, [shp, vp, i, i, i, vp, i, i, sz, i, ip, ip, ip, vp, sz]),
+        "mosaic_host_merge_bounds": (i, [vp, i, vp, i]),
         "mosaic_host_resize_area_u8": (i, [vp, i, i, i, vp, i, i]),
         "mosaic_host_resize_cubic_u8": (i, [vp, i, i, i, vp, i, i]),
         "mosaic_kernel_resize_cubic_u8": (i, [i, vp, i, i, i, vp, i, i]),

@@ -380,6 +380,8 @@ Rect rect_union(const Rect &a, const Rect &b)
 }
 bool rect_eq(const Rect &a, const Rect &b) { return a.x == b.x && a.y == b.y && a.w == b.w && a.h == b.h; }
 
+}  // namespace
+
 // GridBounds::mergeBounds (GridBounds.cpp:39-104), same iteration order
 void merge_bounds(std::vector<Rect> &b)
 {
@@ -413,6 +415,8 @@ void merge_bounds(std::vector<Rect> &b)
         }
     }
 }
+
+namespace {
 
 }  // namespace
 

@@ -48,6 +48,9 @@ void grid_size(const Shape &s, int image_w, int image_h, int pad, int &gx, int &
 Rect rect_at(const Shape &s, int x, int y);                                            // GridUtility.cpp:86-115
 int flip_at(const Shape &s, int x, int y);                                             // GridUtility.cpp:118-132
 
+// GridBounds::mergeBounds (GridBounds.cpp:39-104), same iteration order
+void merge_bounds(std::vector<Rect> &b);
+
 // getCellAt's bound arithmetic (PhotomosaicGeneratorBase.cpp:296-326): detail-space bound of cell (x, y)
 Rect detail_bound(const Shape &normal, int detail_size, double detail, int x, int y, int image_w, int image_h,
                   Rect *clamped_global = nullptr, Rect *local = nullptr);

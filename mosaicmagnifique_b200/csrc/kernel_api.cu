@@ -349,6 +349,28 @@ int mosaic_kernel_resize_cubic_u8(int device, const uint8_t *src, int src_h, int
     return MOSAIC_OK;
 }
 
+int mosaic_host_merge_bounds(const int *rects_xywh, int n, int *out_xywh, int out_capacity)
+{
+    if (n < 0 || (n > 0 && !rects_xywh) || out_capacity < 0 || (out_capacity > 0 && !out_xywh))
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    std::vector<Rect> b((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        b[i].x = rects_xywh[4 * i];
+        b[i].y = rects_xywh[4 * i + 1];
+        b[i].w = rects_xywh[4 * i + 2];
+        b[i].h = rects_xywh[4 * i + 3];
+    }
+    if (!b.empty())
+        merge_bounds(b);
+    for (size_t i = 0; i < b.size() && (int)i < out_capacity; ++i) {
+        out_xywh[4 * i] = b[i].x;
+        out_xywh[4 * i + 1] = b[i].y;
+        out_xywh[4 * i + 2] = b[i].w;
+        out_xywh[4 * i + 3] = b[i].h;
+    }
+    return (int)b.size();
+}
+
 int mosaic_host_resize_cubic_u8(const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w)
 {
     if (!src || !dst)

@@ -22,7 +22,10 @@ Reference citations (all under /root/reference/src):
   .mcs container               CellShape/CellShape.cpp:363-434, Other/CustomQDataStream.h:56-87
 
 Parity pinning: the colour maths is pinned by the reference's 48 known-answer vectors and by
-the reference's own ColourDifference.cpp / GridUtility.cpp compiled unmodified (libref_core.so).
+the reference's own ColourDifference.cpp / GridUtility.cpp / GridBounds.cpp compiled unmodified
+(libref_core.so); the generator loop (generate / generate_step / select_from_D) is pinned on the
+reference's own CPUPhotomosaicGenerator.cpp, compiled unmodified into the same library and run by
+reference_generate() (tests/test_oracle_ref_generator.py).
 The OpenCV numerics (Lab LUT, INTER_AREA, HSV) have no golden vectors in the reference
 ("parity unpinned" for those); cv2 itself is used here, so the oracle is OpenCV by construction.
 """
@@ -570,6 +573,86 @@ def generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid
         if step + 1 < len(grid_states):
             lib_f32 = halve_library(lib_f32)
     return results
+
+
+# ----------------------------------------------------------------------------- the reference's own generator object code
+
+def reference_generator_available() -> bool:
+    so = os.path.join(HERE, "_ref", "libref_core.so")
+    if not os.path.exists(so):
+        return False
+    try:
+        return hasattr(ctypes.CDLL(so), "ref_cpu_generate")
+    except OSError:
+        return False
+
+
+def reference_generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid_states: list,
+                       diff_type: int = RGB_EUCLIDEAN, scheme: int = SCHEME_NONE, repeat_range: int = 0, repeat_addition: int = 0,
+                       shared_buffer_quirk: bool = True):
+    """The reference's OWN CPUPhotomosaicGenerator.cpp (compiled unmodified into oracle/_ref/libref_core.so, recipe
+    oracle/Makefile, harness oracle/ref_generator_harness.cpp) run on the inputs generate() prepares: the loops, the
+    masked / bounded / early-exit sum, the variant order, calculateRepeats and the strict-< argmin come from the
+    reference's object code; the OpenCV preprocessing (cvtColor, resize, getCellAt's crop + resize) is this module's cv2
+    path. Returns (grids per step, emitted progress values)."""
+    mains = [to_working_space(v, diff_type) for v in colour_scheme_variants(main_bgr8, scheme)]
+    lib_f32 = preprocess_library(lib_bgr8, group, diff_type)
+    return reference_generate_prepared(mains, lib_f32, group, grid_states, diff_type, repeat_range, repeat_addition,
+                                       shared_buffer_quirk)
+
+
+def reference_generate_prepared(mains: list, lib_f32: np.ndarray, group: CellGroup, grid_states: list, diff_type: int,
+                                repeat_range: int, repeat_addition: int, shared_buffer_quirk: bool = True, timing: dict | None = None):
+    """reference_generate on already preprocessed inputs (working-space main variants, step-0 library); timing["seconds"]
+    receives the wall time of the reference's generateBestFits() call alone (bench.py's CPU baseline)."""
+    import time
+    R = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_core.so"))
+    V = len(mains)
+    n_steps = len(grid_states)
+    keep = []  # keeps every array alive until the call returns
+
+    def arr(a, dtype):
+        a = np.ascontiguousarray(a, dtype)
+        keep.append(a)
+        return a
+
+    shapes, ds, masks, libs, rows, cols, grids, n_cells, xy, bounds, px = ([] for _ in range(11))
+    for step, gstate in enumerate(grid_states):
+        cells, b, _flips, coords = extract_cells(mains, group, step, gstate, shared_buffer_quirk)
+        dshape = group.detail_cells[step]
+        assert lib_f32.shape[1] == dshape.size, "library / detail-mask size mismatch (SURVEY Q4)"
+        shapes.append(arr(group.cells[step].params(), np.int32))
+        ds.append(dshape.size)
+        masks.append(arr(dshape.masks4(), np.uint8))
+        libs.append(arr(lib_f32, np.float32))
+        rows.append(gstate.shape[0])
+        cols.append(gstate.shape[1])
+        grids.append(arr(gstate, np.int64).copy())
+        n_cells.append(len(cells))
+        xy.append(arr(coords, np.int32))
+        bounds.append(arr(b, np.int32))
+        px.append(arr(cells, np.float32))
+        if step + 1 < n_steps:
+            lib_f32 = halve_library(lib_f32)
+
+    def pp(arrays, ctype):
+        return (ctypes.POINTER(ctype) * len(arrays))(*[a.ctypes.data_as(ctypes.POINTER(ctype)) for a in arrays])
+
+    ia = lambda v: (ctypes.c_int * len(v))(*[int(x) for x in v])  # noqa: E731
+    cap = int(sum(r * c for r, c in zip(rows, cols))) + 8
+    prog = (ctypes.c_int * cap)()
+    R.ref_cpu_generate.restype = ctypes.c_int
+    t0 = time.perf_counter()
+    n = R.ref_cpu_generate(n_steps, int(diff_type), int(repeat_range), int(repeat_addition), int(libs[0].shape[0]), V,
+                           pp(shapes, ctypes.c_int), ia(ds), pp(masks, ctypes.c_uint8), pp(libs, ctypes.c_float), ia(rows), ia(cols),
+                           pp(grids, ctypes.c_longlong), ia(n_cells), pp(xy, ctypes.c_int), pp(bounds, ctypes.c_int),
+                           pp(px, ctypes.c_float), prog, cap)
+    if timing is not None:
+        timing["seconds"] = time.perf_counter() - t0
+    if n < 0:
+        raise RuntimeError("reference generator failed (%d)" % n)
+    assert R.ref_cpu_message_boxes() == 0
+    return grids, list(prog[:min(n, cap)])
 
 
 # ----------------------------------------------------------------------------- buildPhotomosaic

@@ -1,8 +1,9 @@
-// C entry points over the reference's own ColourDifference.cpp and GridUtility.cpp, which
+// C entry points over the reference's own ColourDifference.cpp, GridUtility.cpp and GridBounds.cpp, which
 // oracle/Makefile compiles unmodified from /root/reference into oracle/_ref/libref_core.so.
 // Test infrastructure only: used to validate the oracle's restatement (tests/test_oracle_ref.py).
 #include <optional>
 #include "ColourDifference.h"
+#include "GridBounds.h"
 #include "GridUtility.h"
 
 static CellShape make_shape(const int *p)
@@ -43,5 +44,20 @@ int ref_flip_at(const int *shape, int x, int y)
 {
     const auto f = GridUtility::getFlipStateAt(make_shape(shape), x, y);
     return (f.horizontal ? 1 : 0) + (f.vertical ? 2 : 0);
+}
+// GridBounds::addBound x n, mergeBounds; rects are x, y, w, h quadruples. Returns the number of merged bounds written.
+int ref_merge_bounds(const int *rects, int n, int *out, int out_capacity)
+{
+    GridBounds b;
+    for (int i = 0; i < n; ++i)
+        b.addBound(cv::Rect(rects[4 * i], rects[4 * i + 1], rects[4 * i + 2], rects[4 * i + 3]));
+    if (!b.empty())
+        b.mergeBounds();
+    int m = 0;
+    for (auto it = b.cbegin(); it != b.cend(); ++it, ++m)
+        if (m < out_capacity) {
+            out[4 * m] = it->x; out[4 * m + 1] = it->y; out[4 * m + 2] = it->width; out[4 * m + 3] = it->height;
+        }
+    return m;
 }
 }

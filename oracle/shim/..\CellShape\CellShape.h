@@ -1,5 +1,5 @@
 // Stand-in for the reference's CellShape (src/CellShape/CellShape.h) exposing only the
-// getters GridUtility.cpp reads; found through the reference's Windows-style include
+// getters GridUtility.cpp and CPUPhotomosaicGenerator.cpp read; found through the reference's Windows-style include
 // "..\CellShape\CellShape.h" (a literal file name on Linux).
 #pragma once
 #include <opencv2/core.hpp>
@@ -19,4 +19,10 @@ public:
     bool getAlternateColFlipVertical() const { return colFlipV; }
     bool getAlternateRowFlipHorizontal() const { return rowFlipH; }
     bool getAlternateRowFlipVertical() const { return rowFlipV; }
+    // the four flipped masks, index = horizontal + 2 * vertical (CellShape::getCellMask, CellShape.cpp:138-152)
+    cv::Mat masks[4];
+    const cv::Mat &getCellMask(const bool t_flippedHorizontal, const bool t_flippedVertical) const
+    {
+        return masks[(t_flippedHorizontal ? 1 : 0) + (t_flippedVertical ? 2 : 0)];
+    }
 };

@@ -1,12 +1,19 @@
-// Minimal stand-in for the few OpenCV types the reference's ColourDifference.cpp and
-// GridUtility.cpp touch, so those files can be compiled UNMODIFIED from /root/reference
+// Minimal stand-in for the few OpenCV types the reference's ColourDifference.cpp, GridUtility.cpp
+// and GridBounds.cpp touch, so those files can be compiled UNMODIFIED from /root/reference
 // into oracle/_ref (test infrastructure only; see oracle/Makefile). Not OpenCV code.
 #pragma once
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <vector>
+typedef unsigned char uchar;
 namespace cv {
 template <typename T, int N> struct Vec {
     T val[N];
@@ -21,7 +28,43 @@ typedef Vec<float, 3> Vec3f;
 struct Point { int x = 0, y = 0; };
 struct Rect {
     int x = 0, y = 0, width = 0, height = 0;
+    Rect() {}
+    Rect(int x_, int y_, int w_, int h_) : x(x_), y(y_), width(w_), height(h_) {}
     Point tl() const { return {x, y}; }
     Point br() const { Point p; p.x = x + width; p.y = y + height; return p; }
+    bool empty() const { return width <= 0 || height <= 0; }
+};
+// what GridBounds.cpp needs: equality and the bounding-box union (an empty operand contributes nothing)
+inline bool operator==(const Rect &a, const Rect &b) { return a.x == b.x && a.y == b.y && a.width == b.width && a.height == b.height; }
+inline Rect operator|(const Rect &a, const Rect &b)
+{
+    if (a.empty())
+        return b;
+    if (b.empty())
+        return a;
+    const int x1 = a.x < b.x ? a.x : b.x, y1 = a.y < b.y ? a.y : b.y;
+    const int x2 = a.x + a.width > b.x + b.width ? a.x + a.width : b.x + b.width;
+    const int y2 = a.y + a.height > b.y + b.height ? a.y + a.height : b.y + b.height;
+    return Rect(x1, y1, x2 - x1, y2 - y1);
+}
+struct Scalar {
+    double val[4];
+    Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {}
+};
+// Row-major 2-D array with shared storage: what CPUPhotomosaicGenerator.cpp touches of cv::Mat (rows, cols, ptr<T>(row)).
+// Copies share the buffer, like cv::Mat headers do.
+class Mat {
+public:
+    int rows = 0, cols = 0;
+    Mat() {}
+    Mat(int r, int c, size_t elem_bytes) : rows(r), cols(c), step_(c * elem_bytes), buf_(new unsigned char[(size_t)r * c * elem_bytes], std::default_delete<unsigned char[]>()) {}
+    bool empty() const { return rows == 0 || cols == 0; }
+    unsigned char *data() { return buf_.get(); }
+    const unsigned char *data() const { return buf_.get(); }
+    template <typename T> T *ptr(int row = 0) { return reinterpret_cast<T *>(buf_.get() + (size_t)row * step_); }
+    template <typename T> const T *ptr(int row = 0) const { return reinterpret_cast<const T *>(buf_.get() + (size_t)row * step_); }
+private:
+    size_t step_ = 0;
+    std::shared_ptr<unsigned char> buf_;
 };
 } // namespace cv

@@ -88,6 +88,47 @@ def test_oracle_geometry_matches_compiled_reference(oracle):
         assert (gx.value, gy.value) == oracle.grid_size(sh, 1000, 777)
 
 
+def _bound_sets():
+    """Bound lists of the kind GridGenerator::getGridState feeds to mergeBounds (cell rects of split cells: touching,
+    overlapping, nested, on shifted rows) plus random small rects."""
+    rng = np.random.default_rng(77)
+    sets = [[], [[0, 0, 10, 10]], [[0, 0, 10, 10], [10, 0, 10, 10]], [[0, 0, 10, 10], [0, 10, 10, 10], [0, 21, 10, 10]],
+            [[0, 0, 20, 20], [5, 5, 3, 3]], [[5, 5, 3, 3], [0, 0, 20, 20], [20, 0, 20, 20]]]
+    for _ in range(150):
+        n = int(rng.integers(2, 14))
+        cell = int(rng.integers(2, 9))
+        rects = []
+        for _ in range(n):
+            if rng.random() < 0.7:  # grid-aligned cells, sometimes with the half-cell offset of alternate rows
+                x = int(rng.integers(0, 6)) * cell + (cell // 2 if rng.random() < 0.3 else 0)
+                y = int(rng.integers(0, 6)) * cell
+                rects.append([x, y, cell, cell])
+            else:
+                rects.append([int(v) for v in (rng.integers(-5, 30), rng.integers(-5, 30), rng.integers(1, 15), rng.integers(1, 15))])
+        sets.append(rects)
+    return sets
+
+
+def test_merge_bounds_matches_compiled_reference(L, oracle):
+    """GridBounds::mergeBounds: the product's host model and the oracle against the reference's own GridBounds.cpp compiled
+    unmodified (oracle/_ref/libref_core.so): same bounds in the same order."""
+    so = os.path.join(ROOT, "oracle", "_ref", "libref_core.so")
+    R = ctypes.CDLL(so) if os.path.exists(so) else None
+    for rects in _bound_sets():
+        flat = np.asarray(rects, np.int32).reshape(-1)
+        out = np.zeros(4 * max(len(rects), 1), np.int32)
+        m = L.mosaic_host_merge_bounds(flat.ctypes.data, len(rects), out.ctypes.data, len(rects))
+        mine = out[:4 * m].reshape(-1, 4).tolist()
+        assert mine == [list(r) for r in oracle._merge_bounds([list(r) for r in rects])]
+        if R is not None:
+            ref = np.zeros_like(out)
+            k = R.ref_merge_bounds(flat.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(rects),
+                                   ref.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), len(rects))
+            assert k == m and ref[:4 * k].reshape(-1, 4).tolist() == mine
+    if R is None:
+        pytest.skip("libref_core.so not built: checked against the oracle only")
+
+
 @pytest.mark.parametrize("src,dst,cn", [(512, 128, 1), (512, 100, 1), (128, 64, 1), (128, 25, 3), (64, 48, 3), (96, 32, 3),
                                         (100, 37, 1), (64, 64, 1)])
 def test_host_resize_area_matches_opencv(L, src, dst, cn):
