@@ -587,6 +587,61 @@ def reference_generator_available() -> bool:
         return False
 
 
+_ENTROPY_CB = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int,
+                               ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long)
+
+
+def _view(ptr, rows, cols, stride, channels):
+    """numpy copy of a (rows x cols x channels) 8U view the reference code hands to the callback."""
+    flat = np.ctypeslib.as_array(ptr, shape=((rows - 1) * stride + cols * channels,))
+    return np.lib.stride_tricks.as_strided(flat, (rows, cols, channels), (stride, channels, 1)).copy()
+
+
+def reference_grid_state(group: CellGroup, main_bgr: np.ndarray | None, height: int = 0, width: int = 0) -> list:
+    """GridGenerator::getGridState run from the reference's OWN GridGenerator.cpp (+ GridUtility.cpp, GridBounds.cpp), compiled
+    unmodified into oracle/_ref/libref_core.so. The two OpenCV-backed helpers it calls per candidate cell --
+    ImageUtility::resizeImage and calculateEntropy (ImageUtility.cpp:34-62, 189-242) -- are evaluated by this module's cv2
+    path through a callback; every decision around them (bounds, clipping, in-bound test, detail-space mask window, split /
+    keep, merging) is the reference's object code."""
+    R = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_core.so"))
+
+    def cb(cell_p, rows, cols, stride, th, tw, mask_p, mrows, mcols, mstride):
+        cell = _view(cell_p, rows, cols, stride, 3)
+        mask = _view(mask_p, mrows, mcols, mstride, 1)[..., 0]
+        cell = resize_image_exact(cell, th, tw)
+        if mask.shape != cell.shape[:2]:
+            return 0.0  # "Mask size differs from image", ImageUtility.cpp:196-200
+        return float(entropy(cv2.cvtColor(cell, cv2.COLOR_BGR2GRAY), np.ascontiguousarray(mask)))
+
+    n = group.size_steps + 1
+    keep = [np.ascontiguousarray(group.cells[s].params(), np.int32) for s in range(n)]
+    masks = [np.ascontiguousarray(group.detail_cells[s].masks4(), np.uint8) for s in range(n)]
+    shapes_pp = (ctypes.POINTER(ctypes.c_int) * n)(*[k.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) for k in keep])
+    masks_pp = (ctypes.POINTER(ctypes.c_uint8) * n)(*[m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) for m in masks])
+    ds = (ctypes.c_int * n)(*[group.detail_cells[s].size for s in range(n)])
+    gh = height if main_bgr is None else main_bgr.shape[0]
+    gw = width if main_bgr is None else main_bgr.shape[1]
+    cap = sum(int(np.prod(grid_size(group.cells[s], gw, gh))) for s in range(n)) + 16
+    out = np.empty(cap, np.int64)
+    rows, cols = (ctypes.c_int * n)(), (ctypes.c_int * n)()
+    img = None if main_bgr is None else np.ascontiguousarray(main_bgr, np.uint8)
+    R.ref_grid_state.restype = ctypes.c_int
+    R.ref_grid_state.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
+                                 ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, _ENTROPY_CB, ctypes.c_void_p,
+                                 ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]
+    k = R.ref_grid_state(n, shapes_pp, ds, masks_pp, float(group.detail), None if img is None else img.ctypes.data,
+                         0 if img is None else img.shape[0], 0 if img is None else img.shape[1],
+                         0 if img is None else img.strides[0], int(height), int(width), _ENTROPY_CB(cb), out.ctypes.data, cap,
+                         rows, cols)
+    if k < 0:
+        raise RuntimeError("reference getGridState: output capacity too small")
+    res, off = [], 0
+    for s in range(k):
+        res.append(out[off:off + rows[s] * cols[s]].reshape(rows[s], cols[s]).copy())
+        off += rows[s] * cols[s]
+    return res
+
+
 def reference_generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid_states: list,
                        diff_type: int = RGB_EUCLIDEAN, scheme: int = SCHEME_NONE, repeat_range: int = 0, repeat_addition: int = 0,
                        shared_buffer_quirk: bool = True):

@@ -15,6 +15,7 @@
 #include <tuple>
 
 #include "CPUPhotomosaicGenerator.h"
+#include "GridGenerator.h"
 
 int g_ref_message_boxes = 0;
 
@@ -55,6 +56,24 @@ std::pair<std::vector<cv::Mat>, cv::Rect> PhotomosaicGeneratorBase::getCellAt(co
 {
     const CellEntry &e = g.cells.at(std::make_tuple(t_cellShape.getSize(), x, y));
     return {e.cells, e.bounds};
+}
+// ---- GridGenerator.cpp's two OpenCV-backed helpers: remembered / forwarded to the cv2 callback
+typedef double (*ref_entropy_fn)(const unsigned char *cell, int rows, int cols, long stride, int target_h, int target_w,
+                                 const unsigned char *mask, int mask_rows, int mask_cols, long mask_stride);
+static ref_entropy_fn g_entropy_cb = nullptr;
+static int g_target_h = 0, g_target_w = 0;
+cv::Mat ImageUtility::resizeImage(const cv::Mat &t_img, const int t_targetHeight, const int t_targetWidth, const ResizeType)
+{
+    g_target_h = t_targetHeight;  // the resize itself happens inside the callback (cv2), together with the entropy
+    g_target_w = t_targetWidth;
+    return t_img;
+}
+double ImageUtility::calculateEntropy(const cv::Mat &t_in, const cv::Mat &t_mask)
+{
+    if (t_in.empty())
+        return 0;  // ImageUtility.cpp:191-192
+    return g_entropy_cb(t_in.data(), t_in.rows, t_in.cols, (long)t_in.step(), g_target_h, g_target_w, t_mask.data(), t_mask.rows,
+                        t_mask.cols, (long)t_mask.step());
 }
 bool ImageUtility::batchResizeMat(std::vector<cv::Mat> &t_images, const double)
 {
@@ -155,4 +174,50 @@ int ref_cpu_generate(int n_steps, int diff_type, int repeat_range, int repeat_ad
     return n;
 }
 int ref_cpu_message_boxes(void) { return g_ref_message_boxes; }
+// GridGenerator::getGridState (GridGenerator.cpp:29-110) from the reference's object code.
+//   shapes[s] (11 ints, normal cell of step s), ds[s] + masks[s] (4 x ds x ds u8) for n_steps = size_steps + 1 levels,
+//   detail in (0, 1]; bgr may be NULL (then height / width give the grid area); entropy = cv2-backed callback.
+//   out: steps written back to back (-1 nullopt, 0 valid), step_rows / step_cols per generated step.
+//   Returns the number of generated steps, or -1 when out_capacity is too small.
+int ref_grid_state(int n_steps, const int *const *shapes, const int *ds, const unsigned char *const *masks, double detail,
+                   const unsigned char *bgr, int rows, int cols, long stride, int height, int width, ref_entropy_fn entropy,
+                   long long *out, long long out_capacity, int *step_rows, int *step_cols)
+{
+    g_entropy_cb = entropy;
+    CellGroup group;
+    group.detail = detail;
+    for (int s = 0; s < n_steps; ++s) {
+        CellShape normal, dcell;
+        const int *p = shapes[s];
+        normal.size = p[0]; normal.rowSpacing = p[1]; normal.colSpacing = p[2]; normal.altRowSpacing = p[3];
+        normal.altColSpacing = p[4]; normal.altRowOffset = p[5]; normal.altColOffset = p[6];
+        normal.colFlipH = p[7]; normal.colFlipV = p[8]; normal.rowFlipH = p[9]; normal.rowFlipV = p[10];
+        normal.masks[0] = cv::Mat(1, 1, 1);  // getGridState only asks whether the top mask is empty (:35)
+        dcell = normal;
+        dcell.size = ds[s];
+        for (int f = 0; f < 4; ++f)
+            dcell.masks[f] = mat_from(masks[s] + (size_t)f * ds[s] * ds[s], ds[s], ds[s], 1);
+        group.cells.push_back(normal);
+        group.detailCells.push_back(dcell);
+    }
+    cv::Mat image;
+    if (bgr) {
+        image = cv::Mat(rows, cols, 3);
+        for (int y = 0; y < rows; ++y)
+            std::memcpy(image.ptr<unsigned char>(y), bgr + (size_t)y * stride, (size_t)cols * 3);
+    }
+    const GridUtility::MosaicBestFit state = GridGenerator::getGridState(group, image, height, width);
+    long long used = 0;
+    for (size_t s = 0; s < state.size(); ++s) {
+        const int r = (int)state[s].size(), c = r ? (int)state[s][0].size() : 0;
+        if (used + (long long)r * c > out_capacity)
+            return -1;
+        step_rows[s] = r;
+        step_cols[s] = c;
+        for (int y = 0; y < r; ++y)
+            for (int x = 0; x < c; ++x)
+                out[used++] = state[s][y][x].has_value() ? (long long)state[s][y][x].value() : -1;
+    }
+    return (int)state.size();
+}
 }

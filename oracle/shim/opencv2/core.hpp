@@ -51,20 +51,38 @@ struct Scalar {
     double val[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {}
 };
-// Row-major 2-D array with shared storage: what CPUPhotomosaicGenerator.cpp touches of cv::Mat (rows, cols, ptr<T>(row)).
-// Copies share the buffer, like cv::Mat headers do.
+struct Range {
+    int start = 0, end = 0;
+    Range() {}
+    Range(int s, int e) : start(s), end(e) {}
+};
+// Row-major 2-D array with shared storage: what CPUPhotomosaicGenerator.cpp and GridGenerator.cpp touch of cv::Mat (rows,
+// cols, ptr<T>(row), empty(), channels(), sub-views by Range / Rect). Copies and views share the buffer, like cv::Mat headers.
 class Mat {
 public:
     int rows = 0, cols = 0;
     Mat() {}
-    Mat(int r, int c, size_t elem_bytes) : rows(r), cols(c), step_(c * elem_bytes), buf_(new unsigned char[(size_t)r * c * elem_bytes], std::default_delete<unsigned char[]>()) {}
-    bool empty() const { return rows == 0 || cols == 0; }
-    unsigned char *data() { return buf_.get(); }
-    const unsigned char *data() const { return buf_.get(); }
-    template <typename T> T *ptr(int row = 0) { return reinterpret_cast<T *>(buf_.get() + (size_t)row * step_); }
-    template <typename T> const T *ptr(int row = 0) const { return reinterpret_cast<const T *>(buf_.get() + (size_t)row * step_); }
+    Mat(int r, int c, size_t elem_bytes)
+        : rows(r), cols(c), step_(c * elem_bytes), elem_(elem_bytes),
+          buf_(new unsigned char[(size_t)r * c * elem_bytes + 1], std::default_delete<unsigned char[]>())
+    {}
+    Mat(const Mat &m, const Range &rowRange, const Range &colRange)
+        : rows(rowRange.end - rowRange.start), cols(colRange.end - colRange.start), step_(m.step_), elem_(m.elem_),
+          off_(m.off_ + (size_t)rowRange.start * m.step_ + (size_t)colRange.start * m.elem_), buf_(m.buf_)
+    {}
+    Mat(const Mat &m, const Rect &roi)
+        : rows(roi.height), cols(roi.width), step_(m.step_), elem_(m.elem_),
+          off_(m.off_ + (size_t)roi.y * m.step_ + (size_t)roi.x * m.elem_), buf_(m.buf_)
+    {}
+    bool empty() const { return rows <= 0 || cols <= 0 || !buf_; }
+    int channels() const { return (int)elem_; }  // the shim only ever holds 8U images where channels() is asked
+    size_t step() const { return step_; }
+    unsigned char *data() { return buf_.get() + off_; }
+    const unsigned char *data() const { return buf_.get() + off_; }
+    template <typename T> T *ptr(int row = 0) { return reinterpret_cast<T *>(buf_.get() + off_ + (size_t)row * step_); }
+    template <typename T> const T *ptr(int row = 0) const { return reinterpret_cast<const T *>(buf_.get() + off_ + (size_t)row * step_); }
 private:
-    size_t step_ = 0;
+    size_t step_ = 0, elem_ = 0, off_ = 0;
     std::shared_ptr<unsigned char> buf_;
 };
 } // namespace cv

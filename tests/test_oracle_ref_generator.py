@@ -101,3 +101,46 @@ def test_degenerate_inputs(ref):
     _compare(ref, main, lib, ref.CellShape.square(32), 1, 100, 0, 50, 100000)
     main, lib = _inputs(83, 100, 140, 20, 32)  # one detail pixel per cell
     _compare(ref, main, lib, ref.CellShape.square(32), 0, 3, 0, 2, 10)
+
+
+# ---------------------------------------------------------------- GridGenerator::getGridState from the reference's object code
+
+def _grid_cases(o):
+    from mosaicmagnifique_b200 import synthetic
+    tri = o.CellShape.from_mask(synthetic.triangle_mask(64))
+    tri.row_spacing = tri.alt_row_spacing = 64
+    tri.col_spacing = tri.alt_col_spacing = 32
+    tri.alt_col_flip_v = True
+    tri.alt_row_flip_h = True
+    hx = o.CellShape.from_mask(synthetic.hexagon_mask(128))
+    hx.row_spacing = hx.alt_row_spacing = 96
+    hx.col_spacing = hx.alt_col_spacing = 110
+    hx.alt_row_offset = 55
+    #       shape                       detail steps  h    w   seed
+    return [(o.CellShape.square(64),    100,   2,    256, 384, 51),
+            (o.CellShape.square(64),    50,    2,    300, 410, 52),
+            (o.CellShape.square(32),    100,   0,    130, 170, 53),
+            (tri,                       50,    1,    230, 310, 54),
+            (hx.resized(64),            100,   2,    250, 330, 55),
+            (o.CellShape.square(40),    33,    1,    200, 260, 56),
+            (o.CellShape.square(64),    100,   1,    20,  27,  57)]
+
+
+def test_grid_state_matches_reference_object_code(ref, oracle):
+    """The entropy-split grid state: oracle.grid_state == the reference's GridGenerator.cpp compiled unmodified,
+    for square / flipped / offset shapes, 0-2 size steps, integer and fractional detail, an image smaller than a cell."""
+    from mosaicmagnifique_b200 import synthetic
+    for shape, detail, steps, h, w, seed in _grid_cases(oracle):
+        main = synthetic.make_main_image(h, w, seed, block=32)
+        group = oracle.CellGroup.make(shape, detail, steps)
+        want = oracle.reference_grid_state(group, main)
+        got = oracle.grid_state(group, main)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        # without a main image nothing splits (GridGenerator.cpp:158: the entropy rule needs the image)
+        want0 = oracle.reference_grid_state(group, None, h, w)
+        got0 = oracle.grid_state(group, None, h, w)
+        assert len(got0) == len(want0) == 1 and np.array_equal(got0[0], want0[0])
+    assert any(len(oracle.grid_state(oracle.CellGroup.make(s, d, st), synthetic.make_main_image(h, w, sd, block=32))) > 1
+               for s, d, st, h, w, sd in _grid_cases(oracle) if st > 0), "no case exercised a split"
