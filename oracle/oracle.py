@@ -576,138 +576,205 @@ def generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid
 
 
 # ----------------------------------------------------------------------------- the reference's own generator object code
+#
+# oracle/_ref/libref_core.so holds the reference's PhotomosaicGeneratorBase.cpp, CPUPhotomosaicGenerator.cpp, GridGenerator.cpp,
+# ColourDifference.cpp, GridUtility.cpp and GridBounds.cpp compiled UNMODIFIED (oracle/Makefile, stand-in headers oracle/shim,
+# harness oracle/ref_generator_harness.cpp). OpenCV arithmetic inside them (cvtColor, resize) and the colour-scheme variants
+# are answered by the callbacks below with the real OpenCV (cv2). Everything else -- setters, preprocessing flow, getCellAt,
+# the best-fit loops, repeats, argmin, buildPhotomosaic, getGridState -- runs from the reference's object code.
+
+_CV_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                          ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long)
+_SCHEME_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long,
+                              ctypes.POINTER(ctypes.c_uint8))
+_ref_lib = None
+_ref_callbacks = None  # keeps the ctypes thunks alive
+
+
+def _np_view(ptr, rows, cols, cv_type, step, writable=False):
+    """numpy view of a shim cv::Mat (type code: depth in the low 3 bits -- 0 = 8U, 5 = 32F -- channels - 1 above)."""
+    depth, cn = cv_type & 7, ((cv_type >> 3) & 511) + 1
+    dt = np.uint8 if depth == 0 else np.float32
+    isz = np.dtype(dt).itemsize
+    nbytes = (rows - 1) * step + cols * cn * isz
+    raw = np.ctypeslib.as_array(ptr, shape=(nbytes,))
+    v = np.lib.stride_tricks.as_strided(raw.view(np.uint8), (rows, cols * cn * isz), (step, 1))
+    return v, dt, cn
+
+
+def _cv_callback(op, code, src_p, rows, cols, cv_type, step, dst_p, drows, dcols, dtype, dstep):
+    try:
+        raw, dt, cn = _np_view(src_p, rows, cols, cv_type, step)
+        src = np.ascontiguousarray(raw).view(dt).reshape(rows, cols, cn)
+        if cn == 1:
+            src = src[..., 0]
+        if op == 0:
+            out = cv2.cvtColor(src, code)
+        elif code == cv2.INTER_CUBIC:
+            out = resize_cubic_opencv(src, drows, dcols)
+        else:
+            out = cv2.resize(src, (dcols, drows), interpolation=code)
+        draw, ddt, dcn = _np_view(dst_p, drows, dcols, dtype, dstep)
+        out = np.ascontiguousarray(out, ddt).reshape(drows, dcols * dcn)
+        draw[:] = out.view(np.uint8).reshape(drows, -1)
+        return 0
+    except Exception:  # noqa: BLE001 -- must not propagate through the C frames
+        import traceback
+        traceback.print_exc()
+        return 1
+
+
+def _scheme_callback(scheme, src_p, rows, cols, step, dst_p):
+    try:
+        raw, _, _ = _np_view(src_p, rows, cols, 16, step)  # 16 = CV_8UC3
+        img = np.ascontiguousarray(raw).reshape(rows, cols, 3)
+        variants = colour_scheme_variants(img, scheme)[1:]
+        dst = np.ctypeslib.as_array(dst_p, shape=(len(variants) * rows * cols * 3,))
+        dst[:] = np.concatenate([np.ascontiguousarray(v, np.uint8).reshape(-1) for v in variants]) if variants else dst
+        return 0
+    except Exception:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        return 1
+
 
 def reference_generator_available() -> bool:
     so = os.path.join(HERE, "_ref", "libref_core.so")
     if not os.path.exists(so):
         return False
     try:
-        return hasattr(ctypes.CDLL(so), "ref_cpu_generate")
+        return hasattr(ctypes.CDLL(so), "ref_session_create")
     except OSError:
         return False
 
 
-_ENTROPY_CB = ctypes.CFUNCTYPE(ctypes.c_double, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int,
-                               ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long)
+def _ref():
+    global _ref_lib, _ref_callbacks
+    if _ref_lib is None:
+        R = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_core.so"))
+        vp, i, dbl, lng = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_long
+        R.ref_set_callbacks.argtypes = [_CV_CB, _SCHEME_CB]
+        R.ref_session_create.restype = vp
+        R.ref_session_create.argtypes = [vp, i, i, lng, vp, i, i, i, vp, vp, vp, vp, dbl, i, i, i, i]
+        R.ref_session_destroy.argtypes = [vp]
+        R.ref_session_generate.argtypes = [vp, i, vp, vp, vp, vp, i, vp]
+        R.ref_session_build.argtypes = [vp, vp, vp]
+        R.ref_session_get_cell_at.argtypes = [vp, i, i, i, vp, vp]
+        R.ref_grid_state.argtypes = [i, vp, vp, vp, vp, dbl, vp, i, i, lng, i, i, vp, ctypes.c_longlong, vp, vp]
+        _ref_callbacks = (_CV_CB(_cv_callback), _SCHEME_CB(_scheme_callback))
+        R.ref_set_callbacks(*_ref_callbacks)
+        _ref_lib = R
+    return _ref_lib
 
 
-def _view(ptr, rows, cols, stride, channels):
-    """numpy copy of a (rows x cols x channels) 8U view the reference code hands to the callback."""
-    flat = np.ctypeslib.as_array(ptr, shape=((rows - 1) * stride + cols * channels,))
-    return np.lib.stride_tricks.as_strided(flat, (rows, cols, channels), (stride, channels, 1)).copy()
+def _group_args(group: CellGroup):
+    n = group.size_steps + 1
+    keep = {"shapes": [np.ascontiguousarray(group.cells[s].params(), np.int32) for s in range(n)],
+            "masks": [np.ascontiguousarray(group.cells[s].masks4(), np.uint8) for s in range(n)],
+            "dmasks": [np.ascontiguousarray(group.detail_cells[s].masks4(), np.uint8) for s in range(n)]}
+
+    def pp(arrays):
+        return (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+
+    ds = (ctypes.c_int * n)(*[group.detail_cells[s].size for s in range(n)])
+    return n, keep, pp(keep["shapes"]), pp(keep["masks"]), ds, pp(keep["dmasks"])
+
+
+class ReferenceGenerator:
+    """One CPUPhotomosaicGenerator object of the reference, configured through its own setters."""
+
+    def __init__(self, main_bgr8, lib_bgr8, group: CellGroup, diff_type=RGB_EUCLIDEAN, scheme=SCHEME_NONE, repeat_range=0,
+                 repeat_addition=0):
+        R = _ref()
+        self._main = np.ascontiguousarray(main_bgr8, np.uint8)
+        self._lib = np.ascontiguousarray(lib_bgr8, np.uint8)
+        self.group = group
+        n, self._keep, shapes, masks, ds, dmasks = _group_args(group)
+        self._h = R.ref_session_create(self._main.ctypes.data, self._main.shape[0], self._main.shape[1], self._main.strides[0],
+                                       self._lib.ctypes.data, self._lib.shape[0], self._lib.shape[1] if len(self._lib) else 0, n,
+                                       shapes, masks, ds, dmasks, float(group.detail), int(diff_type), int(scheme),
+                                       int(repeat_range), int(repeat_addition))
+        if not self._h:
+            raise RuntimeError("reference generator: configuration rejected")
+
+    def close(self):
+        if self._h:
+            _ref().ref_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def generate(self, grid_states: list, timing: dict | None = None):
+        """setGridState + generateBestFits + getBestFits: (grids, progress values, getMaxProgress())."""
+        import time
+        n = len(grid_states)
+        grids = [np.ascontiguousarray(g, np.int64).copy() for g in grid_states]
+        rows = (ctypes.c_int * n)(*[g.shape[0] for g in grids])
+        cols = (ctypes.c_int * n)(*[g.shape[1] for g in grids])
+        gp = (ctypes.c_void_p * n)(*[g.ctypes.data for g in grids])
+        cap = int(sum(g.size for g in grids)) + 8
+        prog = (ctypes.c_int * cap)()
+        maxp = ctypes.c_int()
+        t0 = time.perf_counter()
+        k = _ref().ref_session_generate(self._h, n, rows, cols, gp, prog, cap, ctypes.byref(maxp))
+        if timing is not None:
+            timing["seconds"] = time.perf_counter() - t0
+        if k < 0:
+            raise RuntimeError("reference generateBestFits failed (%d)" % k)
+        assert _ref().ref_message_boxes() == 0
+        return grids, list(prog[:min(k, cap)]), maxp.value
+
+    def build_photomosaic(self, background=(0, 0, 0, 0)) -> np.ndarray:
+        out = np.empty(self._main.shape[:2] + (4,), np.uint8)
+        bg = (ctypes.c_double * 4)(*[float(v) for v in background])
+        if _ref().ref_session_build(self._h, bg, out.ctypes.data) != 0:
+            raise RuntimeError("reference buildPhotomosaic failed")
+        return out
+
+    def get_cell_at(self, step: int, x: int, y: int, n_variants: int):
+        ds = self.group.detail_cells[step].size
+        cells = np.empty((n_variants, ds, ds, 3), np.float32)
+        bounds = (ctypes.c_int * 4)()
+        v = _ref().ref_session_get_cell_at(self._h, step, x, y, cells.ctypes.data, bounds)
+        if v != n_variants:
+            raise RuntimeError("reference getCellAt: %d variants" % v)
+        return cells, tuple(bounds)
+
+
+def reference_generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid_states: list,
+                       diff_type: int = RGB_EUCLIDEAN, scheme: int = SCHEME_NONE, repeat_range: int = 0, repeat_addition: int = 0,
+                       timing: dict | None = None):
+    """The reference's own generator end to end (setters, preprocessing, getCellAt, best-fit loops): (grids per step,
+    emitted progress values). timing["seconds"] receives the wall time of setGridState + generateBestFits + getBestFits."""
+    g = ReferenceGenerator(main_bgr8, lib_bgr8, group, diff_type, scheme, repeat_range, repeat_addition)
+    try:
+        grids, progress, _ = g.generate(grid_states, timing)
+        return grids, progress
+    finally:
+        g.close()
 
 
 def reference_grid_state(group: CellGroup, main_bgr: np.ndarray | None, height: int = 0, width: int = 0) -> list:
-    """GridGenerator::getGridState run from the reference's OWN GridGenerator.cpp (+ GridUtility.cpp, GridBounds.cpp), compiled
-    unmodified into oracle/_ref/libref_core.so. The two OpenCV-backed helpers it calls per candidate cell --
-    ImageUtility::resizeImage and calculateEntropy (ImageUtility.cpp:34-62, 189-242) -- are evaluated by this module's cv2
-    path through a callback; every decision around them (bounds, clipping, in-bound test, detail-space mask window, split /
-    keep, merging) is the reference's object code."""
-    R = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_core.so"))
-
-    def cb(cell_p, rows, cols, stride, th, tw, mask_p, mrows, mcols, mstride):
-        cell = _view(cell_p, rows, cols, stride, 3)
-        mask = _view(mask_p, mrows, mcols, mstride, 1)[..., 0]
-        cell = resize_image_exact(cell, th, tw)
-        if mask.shape != cell.shape[:2]:
-            return 0.0  # "Mask size differs from image", ImageUtility.cpp:196-200
-        return float(entropy(cv2.cvtColor(cell, cv2.COLOR_BGR2GRAY), np.ascontiguousarray(mask)))
-
-    n = group.size_steps + 1
-    keep = [np.ascontiguousarray(group.cells[s].params(), np.int32) for s in range(n)]
-    masks = [np.ascontiguousarray(group.detail_cells[s].masks4(), np.uint8) for s in range(n)]
-    shapes_pp = (ctypes.POINTER(ctypes.c_int) * n)(*[k.ctypes.data_as(ctypes.POINTER(ctypes.c_int)) for k in keep])
-    masks_pp = (ctypes.POINTER(ctypes.c_uint8) * n)(*[m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)) for m in masks])
-    ds = (ctypes.c_int * n)(*[group.detail_cells[s].size for s in range(n)])
+    """GridGenerator::getGridState run from the reference's OWN GridGenerator.cpp (+ GridUtility.cpp, GridBounds.cpp)."""
+    R = _ref()
+    n, keep, shapes, masks, ds, dmasks = _group_args(group)
     gh = height if main_bgr is None else main_bgr.shape[0]
     gw = width if main_bgr is None else main_bgr.shape[1]
     cap = sum(int(np.prod(grid_size(group.cells[s], gw, gh))) for s in range(n)) + 16
     out = np.empty(cap, np.int64)
     rows, cols = (ctypes.c_int * n)(), (ctypes.c_int * n)()
     img = None if main_bgr is None else np.ascontiguousarray(main_bgr, np.uint8)
-    R.ref_grid_state.restype = ctypes.c_int
-    R.ref_grid_state.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p,
-                                 ctypes.c_int, ctypes.c_int, ctypes.c_long, ctypes.c_int, ctypes.c_int, _ENTROPY_CB, ctypes.c_void_p,
-                                 ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]
-    k = R.ref_grid_state(n, shapes_pp, ds, masks_pp, float(group.detail), None if img is None else img.ctypes.data,
+    k = R.ref_grid_state(n, shapes, masks, ds, dmasks, float(group.detail), None if img is None else img.ctypes.data,
                          0 if img is None else img.shape[0], 0 if img is None else img.shape[1],
-                         0 if img is None else img.strides[0], int(height), int(width), _ENTROPY_CB(cb), out.ctypes.data, cap,
-                         rows, cols)
+                         0 if img is None else img.strides[0], int(height), int(width), out.ctypes.data, cap, rows, cols)
     if k < 0:
-        raise RuntimeError("reference getGridState: output capacity too small")
+        raise RuntimeError("reference getGridState failed (%d)" % k)
     res, off = [], 0
     for s in range(k):
         res.append(out[off:off + rows[s] * cols[s]].reshape(rows[s], cols[s]).copy())
         off += rows[s] * cols[s]
     return res
-
-
-def reference_generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid_states: list,
-                       diff_type: int = RGB_EUCLIDEAN, scheme: int = SCHEME_NONE, repeat_range: int = 0, repeat_addition: int = 0,
-                       shared_buffer_quirk: bool = True):
-    """The reference's OWN CPUPhotomosaicGenerator.cpp (compiled unmodified into oracle/_ref/libref_core.so, recipe
-    oracle/Makefile, harness oracle/ref_generator_harness.cpp) run on the inputs generate() prepares: the loops, the
-    masked / bounded / early-exit sum, the variant order, calculateRepeats and the strict-< argmin come from the
-    reference's object code; the OpenCV preprocessing (cvtColor, resize, getCellAt's crop + resize) is this module's cv2
-    path. Returns (grids per step, emitted progress values)."""
-    mains = [to_working_space(v, diff_type) for v in colour_scheme_variants(main_bgr8, scheme)]
-    lib_f32 = preprocess_library(lib_bgr8, group, diff_type)
-    return reference_generate_prepared(mains, lib_f32, group, grid_states, diff_type, repeat_range, repeat_addition,
-                                       shared_buffer_quirk)
-
-
-def reference_generate_prepared(mains: list, lib_f32: np.ndarray, group: CellGroup, grid_states: list, diff_type: int,
-                                repeat_range: int, repeat_addition: int, shared_buffer_quirk: bool = True, timing: dict | None = None):
-    """reference_generate on already preprocessed inputs (working-space main variants, step-0 library); timing["seconds"]
-    receives the wall time of the reference's generateBestFits() call alone (bench.py's CPU baseline)."""
-    import time
-    R = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_core.so"))
-    V = len(mains)
-    n_steps = len(grid_states)
-    keep = []  # keeps every array alive until the call returns
-
-    def arr(a, dtype):
-        a = np.ascontiguousarray(a, dtype)
-        keep.append(a)
-        return a
-
-    shapes, ds, masks, libs, rows, cols, grids, n_cells, xy, bounds, px = ([] for _ in range(11))
-    for step, gstate in enumerate(grid_states):
-        cells, b, _flips, coords = extract_cells(mains, group, step, gstate, shared_buffer_quirk)
-        dshape = group.detail_cells[step]
-        assert lib_f32.shape[1] == dshape.size, "library / detail-mask size mismatch (SURVEY Q4)"
-        shapes.append(arr(group.cells[step].params(), np.int32))
-        ds.append(dshape.size)
-        masks.append(arr(dshape.masks4(), np.uint8))
-        libs.append(arr(lib_f32, np.float32))
-        rows.append(gstate.shape[0])
-        cols.append(gstate.shape[1])
-        grids.append(arr(gstate, np.int64).copy())
-        n_cells.append(len(cells))
-        xy.append(arr(coords, np.int32))
-        bounds.append(arr(b, np.int32))
-        px.append(arr(cells, np.float32))
-        if step + 1 < n_steps:
-            lib_f32 = halve_library(lib_f32)
-
-    def pp(arrays, ctype):
-        return (ctypes.POINTER(ctype) * len(arrays))(*[a.ctypes.data_as(ctypes.POINTER(ctype)) for a in arrays])
-
-    ia = lambda v: (ctypes.c_int * len(v))(*[int(x) for x in v])  # noqa: E731
-    cap = int(sum(r * c for r, c in zip(rows, cols))) + 8
-    prog = (ctypes.c_int * cap)()
-    R.ref_cpu_generate.restype = ctypes.c_int
-    t0 = time.perf_counter()
-    n = R.ref_cpu_generate(n_steps, int(diff_type), int(repeat_range), int(repeat_addition), int(libs[0].shape[0]), V,
-                           pp(shapes, ctypes.c_int), ia(ds), pp(masks, ctypes.c_uint8), pp(libs, ctypes.c_float), ia(rows), ia(cols),
-                           pp(grids, ctypes.c_longlong), ia(n_cells), pp(xy, ctypes.c_int), pp(bounds, ctypes.c_int),
-                           pp(px, ctypes.c_float), prog, cap)
-    if timing is not None:
-        timing["seconds"] = time.perf_counter() - t0
-    if n < 0:
-        raise RuntimeError("reference generator failed (%d)" % n)
-    assert R.ref_cpu_message_boxes() == 0
-    return grids, list(prog[:min(n, cap)])
 
 
 # ----------------------------------------------------------------------------- buildPhotomosaic

@@ -1,6 +1,8 @@
-// Minimal stand-in for the few OpenCV types the reference's ColourDifference.cpp, GridUtility.cpp
-// and GridBounds.cpp touch, so those files can be compiled UNMODIFIED from /root/reference
-// into oracle/_ref (test infrastructure only; see oracle/Makefile). Not OpenCV code.
+// Minimal stand-in for the OpenCV types and calls the reference's generator sources touch (ColourDifference.cpp,
+// GridUtility.cpp, GridBounds.cpp, GridGenerator.cpp, CPUPhotomosaicGenerator.cpp, PhotomosaicGeneratorBase.cpp), so those
+// files can be compiled UNMODIFIED from /root/reference into oracle/_ref (test infrastructure only; see oracle/Makefile).
+// Not OpenCV code: cv::Mat here is a typed 2-D array with shared storage and views; anything that is OpenCV ARITHMETIC
+// (cvtColor, resize) is forwarded through a callback to the real OpenCV (cv2) by oracle/oracle.py.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -47,6 +49,11 @@ inline Rect operator|(const Rect &a, const Rect &b)
     const int y2 = a.y + a.height > b.y + b.height ? a.y + a.height : b.y + b.height;
     return Rect(x1, y1, x2 - x1, y2 - y1);
 }
+struct Size {
+    int width = 0, height = 0;
+    Size() {}
+    Size(int w, int h) : width(w), height(h) {}
+};
 struct Scalar {
     double val[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {}
@@ -56,33 +63,153 @@ struct Range {
     Range() {}
     Range(int s, int e) : start(s), end(e) {}
 };
-// Row-major 2-D array with shared storage: what CPUPhotomosaicGenerator.cpp and GridGenerator.cpp touch of cv::Mat (rows,
-// cols, ptr<T>(row), empty(), channels(), sub-views by Range / Rect). Copies and views share the buffer, like cv::Mat headers.
+} // namespace cv
+
+// element type codes: the public encoding of the OpenCV API (depth in the low 3 bits, channels - 1 above)
+#define CV_8U 0
+#define CV_32F 5
+#define CV_CN_SHIFT 3
+#define CV_MAT_DEPTH(flags) ((flags) & 7)
+#define CV_MAT_CN(flags) ((((flags) >> CV_CN_SHIFT) & 511) + 1)
+#define CV_MAKETYPE(depth, cn) (CV_MAT_DEPTH(depth) + (((cn) - 1) << CV_CN_SHIFT))
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
+#define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
+
+namespace cv {
+// Typed row-major 2-D array with shared storage. Copies of a Mat and views (Range / Rect) share the buffer, like cv::Mat
+// headers do -- which is what makes std::vector<cv::Mat>(n, cv::Mat(...)) alias one buffer.
 class Mat {
 public:
     int rows = 0, cols = 0;
     Mat() {}
-    Mat(int r, int c, size_t elem_bytes)
-        : rows(r), cols(c), step_(c * elem_bytes), elem_(elem_bytes),
-          buf_(new unsigned char[(size_t)r * c * elem_bytes + 1], std::default_delete<unsigned char[]>())
-    {}
+    Mat(int r, int c, int type) { create(r, c, type); }
+    Mat(int r, int c, int type, const Scalar &s)
+    {
+        create(r, c, type);
+        const int cn = channels();
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols * cn; ++x) {
+                const double v = s.val[x % cn];
+                if (depth() == CV_8U)
+                    ptr<unsigned char>(y)[x] = (unsigned char)(v < 0 ? 0 : v > 255 ? 255 : std::lrint(v));
+                else
+                    ptr<float>(y)[x] = (float)v;
+            }
+    }
     Mat(const Mat &m, const Range &rowRange, const Range &colRange)
-        : rows(rowRange.end - rowRange.start), cols(colRange.end - colRange.start), step_(m.step_), elem_(m.elem_),
-          off_(m.off_ + (size_t)rowRange.start * m.step_ + (size_t)colRange.start * m.elem_), buf_(m.buf_)
+        : rows(rowRange.end - rowRange.start), cols(colRange.end - colRange.start), type_(m.type_), step_(m.step_),
+          off_(m.off_ + (size_t)rowRange.start * m.step_ + (size_t)colRange.start * m.elemSize()), buf_(m.buf_)
     {}
     Mat(const Mat &m, const Rect &roi)
-        : rows(roi.height), cols(roi.width), step_(m.step_), elem_(m.elem_),
-          off_(m.off_ + (size_t)roi.y * m.step_ + (size_t)roi.x * m.elem_), buf_(m.buf_)
+        : rows(roi.height), cols(roi.width), type_(m.type_), step_(m.step_),
+          off_(m.off_ + (size_t)roi.y * m.step_ + (size_t)roi.x * m.elemSize()), buf_(m.buf_)
     {}
+    static Mat zeros(int r, int c, int type) { return Mat(r, c, type, Scalar(0, 0, 0, 0)); }
+    void create(int r, int c, int type)
+    {
+        rows = r;
+        cols = c;
+        type_ = type;
+        step_ = (size_t)c * elemSize();
+        off_ = 0;
+        buf_.reset(new unsigned char[(size_t)r * step_ + 1], std::default_delete<unsigned char[]>());
+    }
     bool empty() const { return rows <= 0 || cols <= 0 || !buf_; }
-    int channels() const { return (int)elem_; }  // the shim only ever holds 8U images where channels() is asked
+    int type() const { return type_; }
+    int depth() const { return CV_MAT_DEPTH(type_); }
+    int channels() const { return CV_MAT_CN(type_); }
+    size_t elemSize() const { return (size_t)(depth() == CV_8U ? 1 : 4) * channels(); }
     size_t step() const { return step_; }
+    Size size() const { return Size(cols, rows); }
     unsigned char *data() { return buf_.get() + off_; }
     const unsigned char *data() const { return buf_.get() + off_; }
     template <typename T> T *ptr(int row = 0) { return reinterpret_cast<T *>(buf_.get() + off_ + (size_t)row * step_); }
     template <typename T> const T *ptr(int row = 0) const { return reinterpret_cast<const T *>(buf_.get() + off_ + (size_t)row * step_); }
+    Mat operator()(const Range &rowRange, const Range &colRange) const { return Mat(*this, rowRange, colRange); }
+    Mat operator()(const Rect &roi) const { return Mat(*this, roi); }
+    Mat clone() const
+    {
+        Mat m;
+        if (!empty()) {
+            m.create(rows, cols, type_);
+            for (int y = 0; y < rows; ++y)
+                std::memcpy(m.ptr<unsigned char>(y), ptr<unsigned char>(y), (size_t)cols * elemSize());
+        }
+        return m;
+    }
+    // copyTo: into the destination's existing storage when it already has this size and type (that is how writing
+    // through a view works), into fresh storage otherwise; with a mask only the elements whose mask byte is non-zero
+    void copyTo(Mat &dst) const { copy_impl(dst, nullptr); }
+    void copyTo(Mat &&dst) const { copy_impl(dst, nullptr); }
+    void copyTo(Mat &dst, const Mat &mask) const { copy_impl(dst, &mask); }
+    void copyTo(Mat &&dst, const Mat &mask) const { copy_impl(dst, &mask); }
+    // convertTo: 8U -> 32F (dst = float(src) * float(alpha) + float(beta), the arithmetic of OpenCV's cvtScale for this pair)
+    void convertTo(Mat &dst, int rtype, double alpha = 1, double beta = 0) const
+    {
+        if (depth() != CV_8U || CV_MAT_DEPTH(rtype) != CV_32F)
+            throw std::invalid_argument("shim convertTo: only 8U -> 32F");
+        Mat out(rows, cols, CV_MAKETYPE(CV_32F, channels()));
+        const float a = (float)alpha, b = (float)beta;
+        for (int y = 0; y < rows; ++y) {
+            const unsigned char *s = ptr<unsigned char>(y);
+            float *d = out.ptr<float>(y);
+            for (int x = 0; x < cols * channels(); ++x)
+                d[x] = (float)s[x] * a + b;
+        }
+        dst = out;
+    }
+
 private:
-    size_t step_ = 0, elem_ = 0, off_ = 0;
+    void copy_impl(Mat &dst, const Mat *mask) const
+    {
+        if (dst.empty() || dst.rows != rows || dst.cols != cols || dst.type_ != type_) {
+            dst.create(rows, cols, type_);
+            if (mask)
+                for (int y = 0; y < rows; ++y)
+                    std::memset(dst.ptr<unsigned char>(y), 0, (size_t)cols * elemSize());
+        }
+        const size_t es = elemSize();
+        for (int y = 0; y < rows; ++y) {
+            const unsigned char *s = ptr<unsigned char>(y);
+            unsigned char *d = dst.ptr<unsigned char>(y);
+            if (!mask) {
+                std::memmove(d, s, (size_t)cols * es);
+                continue;
+            }
+            const unsigned char *m = mask->ptr<unsigned char>(y);
+            for (int x = 0; x < cols; ++x)
+                if (m[x])
+                    std::memcpy(d + x * es, s + x * es, es);
+        }
+    }
+    int type_ = 0;
+    size_t step_ = 0, off_ = 0;
     std::shared_ptr<unsigned char> buf_;
 };
+
+// conversion / interpolation codes: the public values of the OpenCV API, handed unchanged to cv2 by the callback
+enum ColorConversionCodes { COLOR_BGR2BGRA = 0, COLOR_BGR2GRAY = 6, COLOR_BGR2Lab = 44, COLOR_BGR2HSV_FULL = 66, COLOR_HSV2BGR_FULL = 70 };
+enum InterpolationFlags { INTER_CUBIC = 2, INTER_AREA = 3 };
+// OpenCV arithmetic: evaluated by the real OpenCV through the callback the harness installs (oracle/ref_generator_harness.cpp)
+void cvtColor(const Mat &src, Mat &dst, int code);
+void resize(const Mat &src, Mat &dst, Size dsize, double fx = 0, double fy = 0, int interpolation = 1);
+// 8U element-wise logic (buildPhotomosaic's coverage masks)
+inline void bitwise_or(const Mat &a, const Mat &b, Mat &dst)
+{
+    Mat out = (dst.rows == a.rows && dst.cols == a.cols && dst.type() == a.type() && !dst.empty()) ? dst : Mat(a.rows, a.cols, a.type());
+    for (int y = 0; y < a.rows; ++y)
+        for (size_t x = 0; x < (size_t)a.cols * a.elemSize(); ++x)
+            out.ptr<unsigned char>(y)[x] = a.ptr<unsigned char>(y)[x] | b.ptr<unsigned char>(y)[x];
+    dst = out;
+}
+inline void bitwise_not(const Mat &a, Mat &dst)
+{
+    Mat out = (dst.rows == a.rows && dst.cols == a.cols && dst.type() == a.type() && !dst.empty()) ? dst : Mat(a.rows, a.cols, a.type());
+    for (int y = 0; y < a.rows; ++y)
+        for (size_t x = 0; x < (size_t)a.cols * a.elemSize(); ++x)
+            out.ptr<unsigned char>(y)[x] = (unsigned char)~a.ptr<unsigned char>(y)[x];
+    dst = out;
+}
 } // namespace cv

@@ -144,3 +144,78 @@ def test_grid_state_matches_reference_object_code(ref, oracle):
         assert len(got0) == len(want0) == 1 and np.array_equal(got0[0], want0[0])
     assert any(len(oracle.grid_state(oracle.CellGroup.make(s, d, st), synthetic.make_main_image(h, w, sd, block=32))) > 1
                for s, d, st, h, w, sd in _grid_cases(oracle) if st > 0), "no case exercised a split"
+
+
+# ---------------------------------------------------------------- getCellAt / buildPhotomosaic / getMaxProgress
+
+@pytest.mark.parametrize("diff,detail,scheme", [(2, 100, 0), (0, 50, 0), (1, 30, 0), (0, 100, 2), (2, 50, 1)])
+def test_get_cell_at_matches_reference_object_code(ref, diff, detail, scheme):
+    """getCellAt (PhotomosaicGeneratorBase.cpp:293-329) from the reference's object code on the reference's own
+    preprocessMainImage(): cells (bit for bit, f32) and detail-space bounds equal oracle.extract_cells, for interior,
+    clipped and fully padded cells, fractional detail, and the aliased variants of quirk Q1 (scheme TRIADIC at detail 100)."""
+    from mosaicmagnifique_b200 import synthetic
+    o = ref
+    main = synthetic.make_main_image(150, 210, 91 + diff, block=32)
+    lib = synthetic.make_library(4, 32, 92)
+    sh = o.CellShape.from_mask(synthetic.triangle_mask(64))
+    sh.row_spacing = sh.alt_row_spacing = 64
+    sh.col_spacing = sh.alt_col_spacing = 32
+    sh.alt_col_flip_v = True
+    shape = sh.resized(32)
+    group = o.CellGroup.make(shape, detail, 0)
+    state = o.grid_state(group, main)[0]
+    mains = [o.to_working_space(v, diff) for v in o.colour_scheme_variants(main, scheme)]
+    cells, bounds, _flips, coords = o.extract_cells(mains, group, 0, state)
+    g = o.ReferenceGenerator(main, lib, group, diff, scheme, 0, 0)
+    try:
+        for i in range(len(cells)):
+            c, b = g.get_cell_at(0, int(coords[i][0]), int(coords[i][1]), len(mains))
+            assert b == tuple(int(v) for v in bounds[i])
+            assert np.array_equal(c, cells[i]), "cell %s differs" % (coords[i],)
+    finally:
+        g.close()
+    assert len(cells) > 20
+
+
+def test_build_photomosaic_matches_reference_object_code(ref):
+    """buildPhotomosaic (PhotomosaicGeneratorBase.cpp:110-207) from the reference's object code on its own best fits: the
+    BGRA mosaic equals oracle.build_photomosaic byte for byte (two size levels, non-square cells, a background colour)."""
+    from mosaicmagnifique_b200 import synthetic
+    o = ref
+    main = synthetic.make_main_image(200, 260, 95, block=32)
+    lib = synthetic.make_library(30, 64, 96)
+    hx = o.CellShape.from_mask(synthetic.hexagon_mask(128))
+    hx.row_spacing = hx.alt_row_spacing = 96
+    hx.col_spacing = hx.alt_col_spacing = 110
+    hx.alt_row_offset = 55
+    for shape, steps in ((o.CellShape.square(64), 1), (hx.resized(64), 1), (o.CellShape.square(64), 0)):
+        group = o.CellGroup.make(shape, 100, steps)
+        states = o.grid_state(group, main)
+        g = o.ReferenceGenerator(main, lib, group, 1, 0, 2, 100)
+        try:
+            grids, _, max_progress = g.generate(states)
+            mosaic = g.build_photomosaic((10, 20, 30, 0))
+        finally:
+            g.close()
+        want = o.build_photomosaic(main.shape, lib, group, grids, background=(10, 20, 30, 0))
+        assert np.array_equal(mosaic, want)
+        # getMaxProgress (PhotomosaicGeneratorBase.cpp:210-214): 4^(S-1) * S * cols * rows of step 0
+        S = len(states)
+        assert max_progress == 4 ** (S - 1) * S * states[0].shape[0] * states[0].shape[1]
+
+
+def test_committed_golden_is_reproduced_by_the_reference(ref):
+    """tests/golden/generator_golden.npz (the fixtures the CUDA path is checked against on the GPU box) are oracle outputs;
+    the reference's own object code must reproduce their grids from the recorded inputs."""
+    from tests.test_oracle_pipeline import _golden, golden_case
+    G = _golden()
+    for name in G["names"]:
+        name = str(name)
+        shape, diff, detail, steps, rr, ra, scheme = golden_case(ref, G, name)
+        group = ref.CellGroup.make(shape, detail, steps)
+        states = [G["%s/state%d" % (name, s)] for s in range(steps + 1)]
+        got_states = ref.reference_grid_state(group, G[name + "/main"])
+        assert len(got_states) == len(states) and all(np.array_equal(a, b) for a, b in zip(got_states, states))
+        grids, _ = ref.reference_generate(G[name + "/main"], G[name + "/lib"], group, states, diff, scheme, rr, ra)
+        for s in range(steps + 1):
+            assert np.array_equal(grids[s], G["%s/grid%d" % (name, s)])
