@@ -429,3 +429,69 @@ def test_cuda_path_against_reference_object_code(oracle, case):
             assert np.array_equal(got[s], ref_grids[s])  # no tie-band cell: the grids are simply identical
         n_diff += int((got[s] != ref_grids[s]).sum())
     print("%s: %d cells differ from the reference grid (all inside the tie band)" % (case, n_diff))
+
+
+def _direct_reference_case(oracle, main, lib, shape, diff, detail, steps, rr, ra, scheme=0):
+    """CUDA path vs the reference's object code on one configuration; returns (cells, cells that differ)."""
+    from mosaicmagnifique_b200 import CellGroup, PhotomosaicGenerator
+    group = oracle.CellGroup.make(shape, detail, steps)
+    ref_states = oracle.reference_grid_state(group, main)
+    ref_grids, _ = oracle.reference_generate(main, lib, group, ref_states, diff, scheme, rr, ra)
+    gen = PhotomosaicGenerator(0)
+    gen.setMainImage(main)
+    gen.setLibrary(lib)
+    gen.setColourDifference(diff)
+    gen.setColourScheme(scheme)
+    cg = CellGroup()
+    cg.setCellShape(_to_product_shape(shape))
+    cg.setDetail(detail)
+    cg.setSizeSteps(steps)
+    gen.setCellGroup(cg)
+    states = gen.computeGridState()
+    assert len(states) == len(ref_states) and all(np.array_equal(a, b) for a, b in zip(states, ref_states))
+    gen.setRepeat(rr, ra)
+    assert gen.generateBestFits()
+    got = gen.getBestFits()
+    gen.close()
+    differ = [np.argwhere(g != r) for g, r in zip(got, ref_grids)]
+    n_diff = sum(len(d) for d in differ)
+    if n_diff:
+        # only legitimate inside the tie band: judge on the oracle's f64 sums (its grids equal the reference's)
+        want = oracle.generate(main, lib, group, ref_states, diff, scheme, rr, ra, want_D=True)
+        for s in range(len(ref_states)):
+            assert np.array_equal(want[s].grid, ref_grids[s])
+            _, _, bad = check_grid(want[s].D, ref_states[s], got[s], rr, ra, TOL)
+            assert not bad, "step %d: %s" % (s, bad[:3])
+    return sum(int((r >= 0).sum()) for r in ref_grids), n_diff
+
+
+def test_config1_shape_against_reference_object_code(oracle):
+    """BASELINE.json configs[0] shape (the reference's own CPU-runnable case, tst_Generator.h:238): a 1250 x 1000 main image,
+    214-image library at 128 px (substitute for lib.mil), square cells, RGB Euclidean, repeats (20, 10000),
+    detail 100 % and 50 % -- the CUDA grid against the reference generator's own object code."""
+    if not oracle.reference_generator_available():
+        pytest.skip("oracle/_ref/libref_core.so (reference object code) not present / not loadable")
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(1000, 1250, 401, block=64)
+    lib = synthetic.make_library(214, 128, 402)
+    for detail in (100, 50):
+        n, n_diff = _direct_reference_case(oracle, main, lib, oracle.CellShape.square(128), 0, detail, 0, 20, 10000)
+        assert n == 8 * 10
+        print("config 1 shape, detail %d: %d of %d cells differ from the reference (tie band)" % (detail, n_diff, n))
+
+
+def test_config2_shape_against_reference_object_code(oracle):
+    """BASELINE.json configs[1] shape with a reduced library: CIEDE2000, hexagon cells (Hexagon.mcs proportions) resized to
+    128 px, detail 50 %, odd-row offsets and clipped edge cells -- against the reference generator's own object code."""
+    if not oracle.reference_generator_available():
+        pytest.skip("oracle/_ref/libref_core.so (reference object code) not present / not loadable")
+    from mosaicmagnifique_b200 import synthetic
+    hx = oracle.CellShape.from_mask(synthetic.hexagon_mask(512))
+    hx.row_spacing = hx.alt_row_spacing = 385
+    hx.col_spacing = hx.alt_col_spacing = 440
+    hx.alt_row_offset = 220
+    main = synthetic.make_main_image(800, 1000, 411, block=64)
+    lib = synthetic.make_library(96, 128, 412)
+    n, n_diff = _direct_reference_case(oracle, main, lib, hx.resized(128), 2, 50, 0, 2, 500)
+    assert n > 60
+    print("config 2 shape: %d of %d cells differ from the reference (tie band)" % (n_diff, n))
