@@ -35,8 +35,8 @@ static std::vector<int> g_progress;
 static void call_cv(int op, int code, const cv::Mat &src, cv::Mat &dst, int drows, int dcols, int dtype)
 {
     cv::Mat out(drows, dcols, dtype);  // fresh storage: src and dst may be the same Mat object
-    if (!g_cv || g_cv(op, code, src.data(), src.rows, src.cols, src.type(), (long)src.step(), out.data(), drows, dcols, dtype,
-                      (long)out.step()) != 0)
+    if (!g_cv || g_cv(op, code, src.data, src.rows, src.cols, src.type(), (long)(size_t)src.step, out.data, drows, dcols, dtype,
+                      (long)(size_t)out.step) != 0)
         throw std::runtime_error("OpenCV callback failed");
     dst = out;
 }
@@ -131,7 +131,7 @@ ColourScheme::FunctionType ColourScheme::getFunction(const Type &t_type)
         const int extra = kVariants[scheme] - 1;
         if (extra > 0) {
             cv::Mat all(t_image.rows * extra, t_image.cols, t_image.type());
-            if (!g_scheme || g_scheme(scheme, t_image.data(), t_image.rows, t_image.cols, (long)t_image.step(), all.data()) != 0)
+            if (!g_scheme || g_scheme(scheme, t_image.data, t_image.rows, t_image.cols, (long)(size_t)t_image.step, all.data) != 0)
                 throw std::runtime_error("colour-scheme callback failed");
             for (int v = 0; v < extra; ++v)
                 out.push_back(cv::Mat(all, cv::Range(v * t_image.rows, (v + 1) * t_image.rows), cv::Range(0, t_image.cols)).clone());

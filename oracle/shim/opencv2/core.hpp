@@ -80,9 +80,16 @@ struct Range {
 namespace cv {
 // Typed row-major 2-D array with shared storage. Copies of a Mat and views (Range / Rect) share the buffer, like cv::Mat
 // headers do -- which is what makes std::vector<cv::Mat>(n, cv::Mat(...)) alias one buffer.
+// Public members follow the names callers written against OpenCV use: rows, cols, data, step.
 class Mat {
 public:
+    struct Step {
+        size_t v = 0;
+        operator size_t() const { return v; }
+    };
     int rows = 0, cols = 0;
+    unsigned char *data = nullptr;  // first element of this header (view offset applied)
+    Step step;                      // bytes per row
     Mat() {}
     Mat(int r, int c, int type) { create(r, c, type); }
     Mat(int r, int c, int type, const Scalar &s)
@@ -99,12 +106,13 @@ public:
             }
     }
     Mat(const Mat &m, const Range &rowRange, const Range &colRange)
-        : rows(rowRange.end - rowRange.start), cols(colRange.end - colRange.start), type_(m.type_), step_(m.step_),
-          off_(m.off_ + (size_t)rowRange.start * m.step_ + (size_t)colRange.start * m.elemSize()), buf_(m.buf_)
+        : rows(rowRange.end - rowRange.start), cols(colRange.end - colRange.start),
+          data(m.data ? m.data + (size_t)rowRange.start * m.step + (size_t)colRange.start * m.elemSize() : nullptr), step(m.step),
+          type_(m.type_), buf_(m.buf_)
     {}
     Mat(const Mat &m, const Rect &roi)
-        : rows(roi.height), cols(roi.width), type_(m.type_), step_(m.step_),
-          off_(m.off_ + (size_t)roi.y * m.step_ + (size_t)roi.x * m.elemSize()), buf_(m.buf_)
+        : rows(roi.height), cols(roi.width), data(m.data ? m.data + (size_t)roi.y * m.step + (size_t)roi.x * m.elemSize() : nullptr),
+          step(m.step), type_(m.type_), buf_(m.buf_)
     {}
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type, Scalar(0, 0, 0, 0)); }
     void create(int r, int c, int type)
@@ -112,21 +120,19 @@ public:
         rows = r;
         cols = c;
         type_ = type;
-        step_ = (size_t)c * elemSize();
-        off_ = 0;
-        buf_.reset(new unsigned char[(size_t)r * step_ + 1], std::default_delete<unsigned char[]>());
+        step.v = (size_t)c * elemSize();
+        buf_.reset(new unsigned char[(size_t)r * step.v + 1], std::default_delete<unsigned char[]>());
+        data = buf_.get();
     }
-    bool empty() const { return rows <= 0 || cols <= 0 || !buf_; }
+    bool empty() const { return rows <= 0 || cols <= 0 || !data; }
+    bool isContinuous() const { return step.v == (size_t)cols * elemSize(); }
     int type() const { return type_; }
     int depth() const { return CV_MAT_DEPTH(type_); }
     int channels() const { return CV_MAT_CN(type_); }
     size_t elemSize() const { return (size_t)(depth() == CV_8U ? 1 : 4) * channels(); }
-    size_t step() const { return step_; }
     Size size() const { return Size(cols, rows); }
-    unsigned char *data() { return buf_.get() + off_; }
-    const unsigned char *data() const { return buf_.get() + off_; }
-    template <typename T> T *ptr(int row = 0) { return reinterpret_cast<T *>(buf_.get() + off_ + (size_t)row * step_); }
-    template <typename T> const T *ptr(int row = 0) const { return reinterpret_cast<const T *>(buf_.get() + off_ + (size_t)row * step_); }
+    template <typename T> T *ptr(int row = 0) { return reinterpret_cast<T *>(data + (size_t)row * step.v); }
+    template <typename T> const T *ptr(int row = 0) const { return reinterpret_cast<const T *>(data + (size_t)row * step.v); }
     Mat operator()(const Range &rowRange, const Range &colRange) const { return Mat(*this, rowRange, colRange); }
     Mat operator()(const Rect &roi) const { return Mat(*this, roi); }
     Mat clone() const
@@ -185,7 +191,6 @@ private:
         }
     }
     int type_ = 0;
-    size_t step_ = 0, off_ = 0;
     std::shared_ptr<unsigned char> buf_;
 };
 
