@@ -578,7 +578,7 @@ def generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid
 # ----------------------------------------------------------------------------- the reference's own generator object code
 #
 # oracle/_ref/libref_core.so holds the reference's PhotomosaicGeneratorBase.cpp, CPUPhotomosaicGenerator.cpp, GridGenerator.cpp,
-# ColourDifference.cpp, GridUtility.cpp and GridBounds.cpp compiled UNMODIFIED (oracle/Makefile, stand-in headers oracle/shim,
+# ColourDifference.cpp, GridUtility.cpp, GridBounds.cpp, CellShape.cpp, CellGroup.cpp and ImageLibrary.cpp compiled UNMODIFIED (oracle/Makefile, stand-in headers oracle/shim,
 # harness oracle/ref_generator_harness.cpp). OpenCV arithmetic inside them (cvtColor, resize) and the colour-scheme variants
 # are answered by the callbacks below with the real OpenCV (cv2). Everything else -- setters, preprocessing flow, getCellAt,
 # the best-fit loops, repeats, argmin, buildPhotomosaic, getGridState -- runs from the reference's object code.
@@ -587,8 +587,11 @@ _CV_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINT
                           ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long)
 _SCHEME_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long,
                               ctypes.POINTER(ctypes.c_uint8))
+_CODEC_CB = ctypes.CFUNCTYPE(ctypes.c_long, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_long, ctypes.c_int, ctypes.c_int,
+                             ctypes.c_int, ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int))
 _ref_lib = None
 _ref_callbacks = None  # keeps the ctypes thunks alive
+_codec_pending = {}
 
 
 def _np_view(ptr, rows, cols, cv_type, step, writable=False):
@@ -638,6 +641,37 @@ def _scheme_callback(scheme, src_p, rows, cols, step, dst_p):
         return 1
 
 
+def _codec_callback(op, src_p, n, rows, cols, cv_type, step, dst_p, info_p):
+    """cv::imencode(".png") / cv::imdecode(IMREAD_UNCHANGED) for the reference's CustomQDataStream (two-phase: size, then bytes)."""
+    try:
+        if op == 0:
+            raw, dt, cn = _np_view(src_p, rows, cols, cv_type, step)
+            img = np.ascontiguousarray(raw).view(dt).reshape(rows, cols, cn)
+            ok, buf = cv2.imencode(".png", img[..., 0] if cn == 1 else img)
+            if not ok:
+                return -1
+            _codec_pending["bytes"] = np.ascontiguousarray(buf).reshape(-1)
+            return int(_codec_pending["bytes"].size)
+        if op == 1:
+            np.ctypeslib.as_array(dst_p, shape=(n,))[:] = _codec_pending.pop("bytes")
+            return n
+        if op == 2:
+            img = cv2.imdecode(np.ctypeslib.as_array(src_p, shape=(n,)).copy(), cv2.IMREAD_UNCHANGED)
+            if img is None or img.dtype != np.uint8:
+                return -1
+            img = img.reshape(img.shape[0], img.shape[1], -1)
+            _codec_pending["pixels"] = np.ascontiguousarray(img)
+            info_p[0], info_p[1], info_p[2] = img.shape[0], img.shape[1], (img.shape[2] - 1) << 3  # CV_8UC(n)
+            return 0
+        img = _codec_pending.pop("pixels")
+        np.ctypeslib.as_array(dst_p, shape=(img.size,))[:] = img.reshape(-1)
+        return 0
+    except Exception:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        return -1
+
+
 def reference_generator_available() -> bool:
     so = os.path.join(HERE, "_ref", "libref_core.so")
     if not os.path.exists(so):
@@ -653,31 +687,43 @@ def _ref():
     if _ref_lib is None:
         R = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_core.so"))
         vp, i, dbl, lng = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_long
-        R.ref_set_callbacks.argtypes = [_CV_CB, _SCHEME_CB]
+        R.ref_set_callbacks.argtypes = [_CV_CB, _SCHEME_CB, _CODEC_CB]
         R.ref_session_create.restype = vp
-        R.ref_session_create.argtypes = [vp, i, i, lng, vp, i, i, i, vp, vp, vp, vp, dbl, i, i, i, i]
+        R.ref_session_create.argtypes = [vp, i, i, lng, vp, i, i, vp, vp, i, i, i, i, i, i]
         R.ref_session_destroy.argtypes = [vp]
         R.ref_session_generate.argtypes = [vp, i, vp, vp, vp, vp, i, vp]
         R.ref_session_build.argtypes = [vp, vp, vp]
         R.ref_session_get_cell_at.argtypes = [vp, i, i, i, vp, vp]
-        R.ref_grid_state.argtypes = [i, vp, vp, vp, vp, dbl, vp, i, i, lng, i, i, vp, ctypes.c_longlong, vp, vp]
-        _ref_callbacks = (_CV_CB(_cv_callback), _SCHEME_CB(_scheme_callback))
+        R.ref_grid_state.argtypes = [vp, vp, i, i, vp, i, i, lng, i, i, vp, ctypes.c_longlong, vp, vp]
+        R.ref_cell_group_cell.argtypes = [vp, vp, i, i, i, i, vp, vp, lng]
+        R.ref_cell_shape_resized.argtypes = [vp, vp, i, vp, vp, lng]
+        R.ref_mcs_load.argtypes = [ctypes.c_char_p, vp, vp, lng, ctypes.c_char_p, i]
+        R.ref_mcs_save.argtypes = [ctypes.c_char_p, vp, vp, ctypes.c_char_p]
+        R.ref_library_create.restype = vp
+        R.ref_library_create.argtypes = [i]
+        R.ref_library_destroy.argtypes = [vp]
+        R.ref_library_add.restype = lng
+        R.ref_library_add.argtypes = [vp, vp, i, i, lng, ctypes.c_char_p]
+        R.ref_library_set_image_size.argtypes = [vp, i]
+        R.ref_library_image_size.argtypes = [vp]
+        R.ref_library_count.restype = lng
+        R.ref_library_count.argtypes = [vp]
+        R.ref_library_get.argtypes = [vp, lng, vp, ctypes.c_char_p, i]
+        R.ref_library_remove.argtypes = [vp, lng]
+        R.ref_library_save.argtypes = [vp, ctypes.c_char_p]
+        R.ref_library_load.argtypes = [vp, ctypes.c_char_p]
+        _ref_callbacks = (_CV_CB(_cv_callback), _SCHEME_CB(_scheme_callback), _CODEC_CB(_codec_callback))
         R.ref_set_callbacks(*_ref_callbacks)
         _ref_lib = R
     return _ref_lib
 
 
 def _group_args(group: CellGroup):
-    n = group.size_steps + 1
-    keep = {"shapes": [np.ascontiguousarray(group.cells[s].params(), np.int32) for s in range(n)],
-            "masks": [np.ascontiguousarray(group.cells[s].masks4(), np.uint8) for s in range(n)],
-            "dmasks": [np.ascontiguousarray(group.detail_cells[s].masks4(), np.uint8) for s in range(n)]}
-
-    def pp(arrays):
-        return (ctypes.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
-
-    ds = (ctypes.c_int * n)(*[group.detail_cells[s].size for s in range(n)])
-    return n, keep, pp(keep["shapes"]), pp(keep["masks"]), ds, pp(keep["dmasks"])
+    """What the application hands to CellGroup (setCellShape, setDetail, setSizeSteps): the TOP-LEVEL shape, its mask, the
+    detail level in percent and the number of size steps. The per-step cells are derived by the reference's CellGroup.cpp."""
+    top = group.cells[0]
+    keep = {"shape": np.ascontiguousarray(top.params(), np.int32), "mask": np.ascontiguousarray(top.mask, np.uint8)}
+    return keep, keep["shape"].ctypes.data, keep["mask"].ctypes.data, int(round(group.detail * 100)), int(group.size_steps)
 
 
 class ReferenceGenerator:
@@ -689,11 +735,10 @@ class ReferenceGenerator:
         self._main = np.ascontiguousarray(main_bgr8, np.uint8)
         self._lib = np.ascontiguousarray(lib_bgr8, np.uint8)
         self.group = group
-        n, self._keep, shapes, masks, ds, dmasks = _group_args(group)
+        self._keep, shape, mask, pct, steps = _group_args(group)
         self._h = R.ref_session_create(self._main.ctypes.data, self._main.shape[0], self._main.shape[1], self._main.strides[0],
-                                       self._lib.ctypes.data, self._lib.shape[0], self._lib.shape[1] if len(self._lib) else 0, n,
-                                       shapes, masks, ds, dmasks, float(group.detail), int(diff_type), int(scheme),
-                                       int(repeat_range), int(repeat_addition))
+                                       self._lib.ctypes.data, self._lib.shape[0], self._lib.shape[1] if len(self._lib) else 0,
+                                       shape, mask, pct, steps, int(diff_type), int(scheme), int(repeat_range), int(repeat_addition))
         if not self._h:
             raise RuntimeError("reference generator: configuration rejected")
 
@@ -758,14 +803,15 @@ def reference_generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellG
 def reference_grid_state(group: CellGroup, main_bgr: np.ndarray | None, height: int = 0, width: int = 0) -> list:
     """GridGenerator::getGridState run from the reference's OWN GridGenerator.cpp (+ GridUtility.cpp, GridBounds.cpp)."""
     R = _ref()
-    n, keep, shapes, masks, ds, dmasks = _group_args(group)
+    keep, shape, mask, pct, steps = _group_args(group)
+    n = steps + 1
     gh = height if main_bgr is None else main_bgr.shape[0]
     gw = width if main_bgr is None else main_bgr.shape[1]
     cap = sum(int(np.prod(grid_size(group.cells[s], gw, gh))) for s in range(n)) + 16
     out = np.empty(cap, np.int64)
     rows, cols = (ctypes.c_int * n)(), (ctypes.c_int * n)()
     img = None if main_bgr is None else np.ascontiguousarray(main_bgr, np.uint8)
-    k = R.ref_grid_state(n, shapes, masks, ds, dmasks, float(group.detail), None if img is None else img.ctypes.data,
+    k = R.ref_grid_state(shape, mask, pct, steps, None if img is None else img.ctypes.data,
                          0 if img is None else img.shape[0], 0 if img is None else img.shape[1],
                          0 if img is None else img.strides[0], int(height), int(width), out.ctypes.data, cap, rows, cols)
     if k < 0:
@@ -775,6 +821,118 @@ def reference_grid_state(group: CellGroup, main_bgr: np.ndarray | None, height: 
         res.append(out[off:off + rows[s] * cols[s]].reshape(rows[s], cols[s]).copy())
         off += rows[s] * cols[s]
     return res
+
+
+def _describe_out(size_hint: int):
+    params = np.zeros(11, np.int32)
+    masks = np.zeros(4 * size_hint * size_hint, np.uint8)
+    return params, masks
+
+
+def _shape_from(params, masks, name="") -> CellShape:
+    size = int(params[0])
+    m4 = masks[:4 * size * size].reshape(4, size, size)
+    sh = CellShape.from_mask(m4[0].copy())
+    (sh.row_spacing, sh.col_spacing, sh.alt_row_spacing, sh.alt_col_spacing, sh.alt_row_offset, sh.alt_col_offset) = \
+        (int(v) for v in params[1:7])
+    sh.alt_col_flip_h, sh.alt_col_flip_v, sh.alt_row_flip_h, sh.alt_row_flip_v = (bool(v) for v in params[7:11])
+    sh.name = name
+    return sh, m4
+
+
+def reference_cell_group_cell(group: CellGroup, step: int, detail: bool):
+    """Cell `step` (normal or detail) of the CellGroup the reference's own CellGroup.cpp / CellShape.cpp derive from the top-level
+    shape: (CellShape, masks4 as the reference's getCellMask returns them)."""
+    keep, shape, mask, pct, steps = _group_args(group)
+    params, masks = _describe_out(group.cells[0].size)
+    if _ref().ref_cell_group_cell(shape, mask, pct, steps, step, int(detail), params.ctypes.data, masks.ctypes.data, masks.size) < 0:
+        raise RuntimeError("reference CellGroup failed")
+    return _shape_from(params, masks)
+
+
+def reference_cell_shape_resized(shape: CellShape, new_size: int):
+    p = np.ascontiguousarray(shape.params(), np.int32)
+    m = np.ascontiguousarray(shape.mask, np.uint8)
+    params, masks = _describe_out(max(new_size, 1))
+    if _ref().ref_cell_shape_resized(p.ctypes.data, m.ctypes.data, int(new_size), params.ctypes.data, masks.ctypes.data, masks.size) < 0:
+        raise RuntimeError("reference CellShape::resized failed")
+    return _shape_from(params, masks)
+
+
+def reference_load_mcs(path: str):
+    """CellShape::loadFromFile of the reference (CellShape.cpp:363-434, through its CustomQDataStream.h)."""
+    params, masks = _describe_out(2048)
+    name = ctypes.create_string_buffer(1024)
+    rc = _ref().ref_mcs_load(path.encode(), params.ctypes.data, masks.ctypes.data, masks.size, name, 1024)
+    if rc == -1:
+        raise ValueError("the reference rejected the .mcs (std::invalid_argument)")
+    if rc < 0:
+        raise RuntimeError("reference loadFromFile failed")
+    return _shape_from(params, masks, name.value.decode())
+
+
+def reference_save_mcs(path: str, shape: CellShape, name: str = ""):
+    p = np.ascontiguousarray(shape.params(), np.int32)
+    m = np.ascontiguousarray(shape.mask, np.uint8)
+    if _ref().ref_mcs_save(path.encode(), p.ctypes.data, m.ctypes.data, name.encode()) != 0:
+        raise RuntimeError("reference saveToFile failed")
+
+
+class ReferenceImageLibrary:
+    """The reference's own ImageLibrary object (ImageLibrary.cpp compiled unmodified)."""
+
+    def __init__(self, image_size: int):
+        self._h = _ref().ref_library_create(int(image_size))
+
+    def close(self):
+        if self._h:
+            _ref().ref_library_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def add_image(self, im: np.ndarray, name: str = "") -> int:
+        im = np.ascontiguousarray(im, np.uint8)
+        empty = im.size == 0
+        idx = _ref().ref_library_add(self._h, None if empty else im.ctypes.data, 0 if empty else im.shape[0],
+                                     0 if empty else im.shape[1], 0 if empty else im.strides[0], name.encode())
+        if idx == -1:
+            raise ValueError("t_im was empty.")
+        if idx < 0:
+            raise RuntimeError("reference addImage failed")
+        return int(idx)
+
+    def set_image_size(self, size: int):
+        assert _ref().ref_library_set_image_size(self._h, int(size)) == 0
+
+    def image_size(self) -> int:
+        return _ref().ref_library_image_size(self._h)
+
+    def items(self):
+        """[(name, image)] in library order."""
+        size, out = self.image_size(), []
+        for i in range(_ref().ref_library_count(self._h)):
+            img = np.empty((size, size, 3), np.uint8)
+            name = ctypes.create_string_buffer(1024)
+            got = _ref().ref_library_get(self._h, i, img.ctypes.data, name, 1024)
+            assert got == size, (got, size)
+            out.append((name.value.decode(), img))
+        return out
+
+    def remove(self, i: int):
+        assert _ref().ref_library_remove(self._h, i) == 0
+
+    def save(self, path: str):
+        if _ref().ref_library_save(self._h, path.encode()) != 0:
+            raise RuntimeError("reference ImageLibrary::saveToFile failed")
+
+    def load(self, path: str):
+        rc = _ref().ref_library_load(self._h, path.encode())
+        if rc == -1:
+            raise ValueError("the reference rejected the .mil (std::invalid_argument)")
+        if rc != 0:
+            raise RuntimeError("reference ImageLibrary::loadFromFile failed")
 
 
 # ----------------------------------------------------------------------------- buildPhotomosaic

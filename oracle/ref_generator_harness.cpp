@@ -12,13 +12,17 @@
 //   * ImageUtility.cpp (Qt GUI types, CUDA warping) and ColourScheme.cpp (cv::Mat_ / forEach templates) cannot be compiled
 //     against the stand-ins: the five ImageUtility functions the generator calls are restated below line by line, and the
 //     colour-scheme variants come from the oracle's cv2 restatement through a second callback;
-//   * CellShape / CellGroup are plain holders of the masks and tiling parameters the oracle derives (their resizing is
-//     cv::resize + threshold, pinned separately against cv2).
+//   * cv::imencode / cv::imdecode (the PNG payload of .mcs / .mil) are the real OpenCV codec through a third callback.
+// Also reference object code in the library: CellShape.cpp, CellGroup.cpp (per-step cell derivation, .mcs load / save through
+// the reference's CustomQDataStream.h) and ImageLibrary.cpp (addImage, setImageSize, .mil load / save), on the Qt stand-ins of
+// oracle/shim/qt_standins.h.
 #include <cstdint>
 #include <cstring>
 
 #include "CPUPhotomosaicGenerator.h"
 #include "GridGenerator.h"
+#include "ImageLibrary.h"
+#include "ref_group.h"
 
 int g_ref_message_boxes = 0;
 
@@ -54,6 +58,34 @@ void cv::resize(const cv::Mat &src, cv::Mat &dst, cv::Size dsize, double, double
     call_cv(1, interpolation, src, dst, dsize.height, dsize.width, src.type());
 }
 
+// ---- PNG codec (imgcodecs) through the real OpenCV
+//   op 0: encode `src` (rows x cols, type, step) as PNG, returns the byte count; op 1: copy the pending bytes to dst;
+//   op 2: decode the n bytes at src, info = {rows, cols, type}; op 3: copy the pending pixels to dst (contiguous)
+typedef long (*ref_codec_fn)(int op, const unsigned char *src, long n, int rows, int cols, int type, long step, unsigned char *dst,
+                             int *info);
+static ref_codec_fn g_codec = nullptr;
+bool cv::imencode(const std::string &, const cv::Mat &img, std::vector<uchar> &buf)
+{
+    if (!g_codec)
+        throw std::runtime_error("no codec callback");
+    const long n = g_codec(0, img.data, 0, img.rows, img.cols, img.type(), (long)(size_t)img.step, nullptr, nullptr);
+    if (n < 0)
+        return false;
+    buf.resize((size_t)n);
+    return g_codec(1, nullptr, n, 0, 0, 0, 0, buf.data(), nullptr) == n;
+}
+cv::Mat cv::imdecode(const std::vector<uchar> &buf, int)
+{
+    if (!g_codec)
+        throw std::runtime_error("no codec callback");
+    int info[3] = {0, 0, 0};
+    if (g_codec(2, buf.data(), (long)buf.size(), 0, 0, 0, 0, nullptr, info) < 0)
+        return cv::Mat();
+    cv::Mat m(info[0], info[1], info[2]);
+    g_codec(3, nullptr, 0, info[0], info[1], info[2], (long)(size_t)m.step, m.data, nullptr);
+    return m;
+}
+
 // ---- ImageUtility, restated (the reference file cannot be compiled here, see the header comment)
 // ImageUtility.cpp:34-62
 cv::Mat ImageUtility::resizeImage(const cv::Mat &t_img, const int t_targetHeight, const int t_targetWidth, const ResizeType t_type)
@@ -84,6 +116,37 @@ bool ImageUtility::batchResizeMat(std::vector<cv::Mat> &t_images, const double t
         im = resizeImage(im, h, w, ResizeType::EXACT);
     return true;
 }
+// ImageUtility.cpp:66-85 (the CPU branch)
+void ImageUtility::batchResizeMat(const std::vector<cv::Mat> &t_src, std::vector<cv::Mat> &t_dst, const int t_targetHeight,
+                                  const int t_targetWidth, const ResizeType t_type, QProgressBar *)
+{
+    t_dst.resize(t_src.size());
+    for (size_t i = 0; i < t_src.size(); ++i)
+        t_dst.at(i) = resizeImage(t_src.at(i), t_targetHeight, t_targetWidth, t_type);
+}
+// ImageUtility.cpp:249-276
+void ImageUtility::imageToSquare(cv::Mat &t_img, const SquareMethod t_method)
+{
+    if (t_img.cols == t_img.rows)
+        return;
+    if (t_method == SquareMethod::CROP) {
+        if (t_img.cols < t_img.rows) {
+            const int diff = (t_img.rows - t_img.cols) / 2;
+            t_img = t_img(cv::Range(diff, t_img.cols + diff), cv::Range(0, t_img.cols));
+        } else {
+            const int diff = (t_img.cols - t_img.rows) / 2;
+            t_img = t_img(cv::Range(0, t_img.rows), cv::Range(diff, t_img.rows + diff));
+        }
+    } else {  // PAD: copyMakeBorder(0, newSize - rows, 0, newSize - cols, BORDER_CONSTANT, 0)
+        const int newSize = std::max(t_img.cols, t_img.rows);
+        cv::Mat result = cv::Mat::zeros(newSize, newSize, t_img.type());
+        t_img.copyTo(result(cv::Rect(0, 0, t_img.cols, t_img.rows)));
+        t_img = result;
+    }
+}
+// GUI-only edge cells (CellGroup.cpp:33-48, 115-126): a plain copy stands in for the edge-detected, transparent overlay
+void ImageUtility::edgeDetect(const cv::Mat &t_src, cv::Mat &t_dst) { t_dst = t_src.clone(); }
+void ImageUtility::matMakeTransparent(const cv::Mat &t_src, cv::Mat &t_dst, const int) { t_dst = t_src.clone(); }
 // ImageUtility.cpp:173-186 (split + constant 255 plane + merge = BGR -> BGRA)
 void ImageUtility::addAlphaChannel(std::vector<cv::Mat> &t_images)
 {
@@ -144,40 +207,6 @@ ColourScheme::FunctionType ColourScheme::getFunction(const Type &t_type)
 void PhotomosaicGeneratorBase::progress(const int t_progressStep) { g_progress.push_back(t_progressStep); }
 
 namespace {
-cv::Mat mat_from(const void *src, int rows, int cols, int type, size_t src_step = 0)
-{
-    cv::Mat m(rows, cols, type);
-    const size_t row_bytes = (size_t)cols * m.elemSize();
-    for (int y = 0; y < rows; ++y)
-        std::memcpy(m.ptr<unsigned char>(y), (const unsigned char *)src + (size_t)y * (src_step ? src_step : row_bytes), row_bytes);
-    return m;
-}
-
-// shapes[s]: 11 ints of the NORMAL cell of step s; masks4[s]: 4 x S x S u8 (index flip_h + 2 flip_v) of the normal cell;
-// dmasks4[s]: 4 x ds x ds of the detail cell
-CellGroup make_group(int n_steps, const int *const *shapes, const unsigned char *const *masks4, const int *ds,
-                     const unsigned char *const *dmasks4, double detail)
-{
-    CellGroup group;
-    group.detail = detail;
-    for (int s = 0; s < n_steps; ++s) {
-        CellShape normal;
-        const int *p = shapes[s];
-        normal.size = p[0]; normal.rowSpacing = p[1]; normal.colSpacing = p[2]; normal.altRowSpacing = p[3];
-        normal.altColSpacing = p[4]; normal.altRowOffset = p[5]; normal.altColOffset = p[6];
-        normal.colFlipH = p[7]; normal.colFlipV = p[8]; normal.rowFlipH = p[9]; normal.rowFlipV = p[10];
-        CellShape dcell = normal;
-        dcell.size = ds[s];
-        for (int f = 0; f < 4; ++f) {
-            normal.masks[f] = mat_from(masks4[s] + (size_t)f * p[0] * p[0], p[0], p[0], CV_8UC1);
-            dcell.masks[f] = mat_from(dmasks4[s] + (size_t)f * ds[s] * ds[s], ds[s], ds[s], CV_8UC1);
-        }
-        group.cells.push_back(normal);
-        group.detailCells.push_back(dcell);
-    }
-    return group;
-}
-
 struct Runner : public CPUPhotomosaicGenerator {
     using PhotomosaicGeneratorBase::getCellAt;
     using PhotomosaicGeneratorBase::preprocessMainImage;
@@ -191,25 +220,25 @@ struct Session {
 }  // namespace
 
 extern "C" {
-void ref_set_callbacks(ref_cv_fn cv_cb, ref_scheme_fn scheme_cb)
+void ref_set_callbacks(ref_cv_fn cv_cb, ref_scheme_fn scheme_cb, ref_codec_fn codec_cb)
 {
     g_cv = cv_cb;
     g_scheme = scheme_cb;
+    g_codec = codec_cb;
 }
 
 // A generator object configured like MainWindow.cpp:584-607 / tst_Generator.h:111-136 does it.
 void *ref_session_create(const unsigned char *bgr, int rows, int cols, long stride, const unsigned char *lib, int n_lib, int lib_size,
-                         int n_steps, const int *const *shapes, const unsigned char *const *masks4, const int *ds,
-                         const unsigned char *const *dmasks4, double detail, int diff_type, int scheme, int repeat_range,
-                         int repeat_addition)
+                         const int *shape, const unsigned char *mask, int detail_percent, int size_steps, int diff_type, int scheme,
+                         int repeat_range, int repeat_addition)
 {
     try {
         Session *s = new Session;
-        s->group = make_group(n_steps, shapes, masks4, ds, dmasks4, detail);
-        s->gen.setMainImage(mat_from(bgr, rows, cols, CV_8UC3, (size_t)stride));
+        s->group = ref_make_group(shape, mask, detail_percent, size_steps);
+        s->gen.setMainImage(ref_mat_from(bgr, rows, cols, CV_8UC3, (size_t)stride));
         std::vector<cv::Mat> library;
         for (int i = 0; i < n_lib; ++i)
-            library.push_back(mat_from(lib + (size_t)i * lib_size * lib_size * 3, lib_size, lib_size, CV_8UC3));
+            library.push_back(ref_mat_from(lib + (size_t)i * lib_size * lib_size * 3, lib_size, lib_size, CV_8UC3));
         s->gen.setLibrary(library);
         s->gen.setColourDifference(static_cast<ColourDifference::Type>(diff_type));
         s->gen.setColourScheme(static_cast<ColourScheme::Type>(scheme));
@@ -299,15 +328,14 @@ int ref_session_get_cell_at(void *h, int step, int x, int y, float *cells_out, i
 
 // GridGenerator::getGridState (GridGenerator.cpp:29-110). bgr may be NULL (then height / width give the grid area).
 // out: steps written back to back (-1 nullopt, 0 valid). Returns the number of generated steps, -1 when out is too small.
-int ref_grid_state(int n_steps, const int *const *shapes, const unsigned char *const *masks4, const int *ds,
-                   const unsigned char *const *dmasks4, double detail, const unsigned char *bgr, int rows, int cols, long stride,
-                   int height, int width, long long *out, long long out_capacity, int *step_rows, int *step_cols)
+int ref_grid_state(const int *shape, const unsigned char *mask, int detail_percent, int size_steps, const unsigned char *bgr, int rows,
+                   int cols, long stride, int height, int width, long long *out, long long out_capacity, int *step_rows, int *step_cols)
 {
     try {
-        const CellGroup group = make_group(n_steps, shapes, masks4, ds, dmasks4, detail);
+        const CellGroup group = ref_make_group(shape, mask, detail_percent, size_steps);
         cv::Mat image;
         if (bgr)
-            image = mat_from(bgr, rows, cols, CV_8UC3, (size_t)stride);
+            image = ref_mat_from(bgr, rows, cols, CV_8UC3, (size_t)stride);
         const GridUtility::MosaicBestFit state = GridGenerator::getGridState(group, image, height, width);
         long long used = 0;
         for (size_t s = 0; s < state.size(); ++s) {
@@ -321,6 +349,155 @@ int ref_grid_state(int n_steps, const int *const *shapes, const unsigned char *c
                     out[used++] = state[s][y][x].has_value() ? (long long)state[s][y][x].value() : -1;
         }
         return (int)state.size();
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+
+// ---- CellShape / CellGroup (src/CellShape/CellShape.cpp, CellGroup.cpp)
+static void describe(const CellShape &c, int *params, unsigned char *mask4, long mask_capacity)
+{
+    params[0] = c.getSize(); params[1] = c.getRowSpacing(); params[2] = c.getColSpacing();
+    params[3] = c.getAlternateRowSpacing(); params[4] = c.getAlternateColSpacing();
+    params[5] = c.getAlternateRowOffset(); params[6] = c.getAlternateColOffset();
+    params[7] = c.getAlternateColFlipHorizontal(); params[8] = c.getAlternateColFlipVertical();
+    params[9] = c.getAlternateRowFlipHorizontal(); params[10] = c.getAlternateRowFlipVertical();
+    const long n = (long)c.getSize() * c.getSize();
+    for (int f = 0; f < 4 && mask4 && (f + 1) * n <= mask_capacity; ++f) {
+        const cv::Mat &m = c.getCellMask(f & 1, (f >> 1) & 1);  // index flip_h + 2 flip_v
+        for (int y = 0; y < m.rows; ++y)
+            std::memcpy(mask4 + f * n + (long)y * m.cols, m.ptr<unsigned char>(y), (size_t)m.cols);
+    }
+}
+// the normal (detail = 0) or detail (detail = 1) cell of size step `step` of the group the application would build:
+// params = 11 ints, mask4 = 4 x size x size (may be NULL). Returns the cell size, -3 on an exception.
+int ref_cell_group_cell(const int *shape, const unsigned char *mask, int detail_percent, int size_steps, int step, int detail,
+                        int *params, unsigned char *mask4, long mask_capacity)
+{
+    try {
+        const CellGroup group = ref_make_group(shape, mask, detail_percent, size_steps);
+        describe(group.getCell((size_t)step, detail != 0), params, mask4, mask_capacity);
+        return params[0];
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+// CellShape::resized (CellShape.cpp:281-312)
+int ref_cell_shape_resized(const int *shape, const unsigned char *mask, int new_size, int *params, unsigned char *mask4, long mask_capacity)
+{
+    try {
+        describe(ref_make_shape(shape, mask).resized(new_size), params, mask4, mask_capacity);
+        return params[0];
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+// CellShape::loadFromFile (CellShape.cpp:363-434): params + the four masks of the stored shape; name_utf8 receives the name.
+// Returns the cell size, -1 when the reference throws std::invalid_argument, -3 on any other exception.
+int ref_mcs_load(const char *path, int *params, unsigned char *mask4, long mask_capacity, char *name_utf8, int name_capacity)
+{
+    try {
+        CellShape c;
+        c.loadFromFile(QString(path));
+        describe(c, params, mask4, mask_capacity);
+        if (name_utf8 && name_capacity > 0) {
+            std::strncpy(name_utf8, c.getName().toStdString().c_str(), (size_t)name_capacity - 1);
+            name_utf8[name_capacity - 1] = 0;
+        }
+        return params[0];
+    } catch (const std::invalid_argument &) {
+        return -1;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+// CellShape::saveToFile (CellShape.cpp:321-360)
+int ref_mcs_save(const char *path, const int *shape, const unsigned char *mask, const char *name_utf8)
+{
+    try {
+        CellShape c = ref_make_shape(shape, mask);
+        c.setName(QString::fromStdString(name_utf8 ? name_utf8 : ""));
+        c.saveToFile(QString(path));
+        return 0;
+    } catch (const std::invalid_argument &) {
+        return -1;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+
+// ---- ImageLibrary (src/ImageLibrary/ImageLibrary.cpp)
+void *ref_library_create(int image_size) { return new ImageLibrary((size_t)image_size); }
+void ref_library_destroy(void *h) { delete static_cast<ImageLibrary *>(h); }
+// addImage (ImageLibrary.cpp:62-86): returns the (random) index the image was inserted at, -1 for an empty image
+long ref_library_add(void *h, const unsigned char *bgr, int rows, int cols, long stride, const char *name_utf8)
+{
+    try {
+        cv::Mat im;
+        if (bgr && rows > 0 && cols > 0)
+            im = ref_mat_from(bgr, rows, cols, CV_8UC3, (size_t)stride);
+        return (long)static_cast<ImageLibrary *>(h)->addImage(im, QString::fromStdString(name_utf8 ? name_utf8 : ""));
+    } catch (const std::invalid_argument &) {
+        return -1;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+int ref_library_set_image_size(void *h, int size)
+{
+    try {
+        static_cast<ImageLibrary *>(h)->setImageSize((size_t)size);
+        return 0;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+int ref_library_image_size(void *h) { return (int)static_cast<ImageLibrary *>(h)->getImageSize(); }
+long ref_library_count(void *h) { return (long)static_cast<ImageLibrary *>(h)->getImages().size(); }
+// image i (size x size x 3, contiguous) and its name
+int ref_library_get(void *h, long i, unsigned char *out, char *name_utf8, int name_capacity)
+{
+    try {
+        const ImageLibrary *lib = static_cast<ImageLibrary *>(h);
+        const cv::Mat &m = lib->getImages().at((size_t)i);
+        for (int y = 0; y < m.rows; ++y)
+            std::memcpy(out + (size_t)y * m.cols * 3, m.ptr<unsigned char>(y), (size_t)m.cols * 3);
+        if (name_utf8 && name_capacity > 0) {
+            std::strncpy(name_utf8, lib->getNames().at((size_t)i).toStdString().c_str(), (size_t)name_capacity - 1);
+            name_utf8[name_capacity - 1] = 0;
+        }
+        return m.rows;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+int ref_library_remove(void *h, long i)
+{
+    try {
+        static_cast<ImageLibrary *>(h)->removeAtIndex((size_t)i);
+        return 0;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+int ref_library_save(void *h, const char *path)
+{
+    try {
+        static_cast<ImageLibrary *>(h)->saveToFile(QString(path));
+        return 0;
+    } catch (const std::invalid_argument &) {
+        return -1;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
+int ref_library_load(void *h, const char *path)
+{
+    try {
+        static_cast<ImageLibrary *>(h)->loadFromFile(QString(path));
+        return 0;
+    } catch (const std::invalid_argument &) {
+        return -1;
     } catch (const std::exception &) {
         return -3;
     }

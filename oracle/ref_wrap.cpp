@@ -5,15 +5,9 @@
 #include "ColourDifference.h"
 #include "GridBounds.h"
 #include "GridUtility.h"
+#include "ref_group.h"
 
-static CellShape make_shape(const int *p)
-{
-    CellShape s;
-    s.size = p[0]; s.rowSpacing = p[1]; s.colSpacing = p[2]; s.altRowSpacing = p[3]; s.altColSpacing = p[4];
-    s.altRowOffset = p[5]; s.altColOffset = p[6];
-    s.colFlipH = p[7]; s.colFlipV = p[8]; s.rowFlipH = p[9]; s.rowFlipV = p[10];
-    return s;
-}
+static CellShape make_shape(const int *p) { return ref_make_shape(p, nullptr); }
 
 extern "C" {
 double ref_rgb_euclidean(const double *a, const double *b)

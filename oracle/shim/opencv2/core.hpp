@@ -57,6 +57,7 @@ struct Size {
 struct Scalar {
     double val[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {}
+    double operator[](int i) const { return val[i]; }
 };
 struct Range {
     int start = 0, end = 0;
@@ -87,11 +88,31 @@ public:
         size_t v = 0;
         operator size_t() const { return v; }
     };
+    // `m.size` is an object in OpenCV (compared with != and called as m.size()): it looks at its owner's rows / cols
+    struct MatSize {
+        const Mat *owner;
+        explicit MatSize(const Mat *o) : owner(o) {}
+        Size operator()() const { return Size(owner->cols, owner->rows); }
+        bool operator==(const MatSize &o) const { return owner->rows == o.owner->rows && owner->cols == o.owner->cols; }
+        bool operator!=(const MatSize &o) const { return !(*this == o); }
+    };
     int rows = 0, cols = 0;
     unsigned char *data = nullptr;  // first element of this header (view offset applied)
     Step step;                      // bytes per row
+    MatSize size{this};
     Mat() {}
+    Mat(const Mat &m) : rows(m.rows), cols(m.cols), data(m.data), step(m.step), type_(m.type_), buf_(m.buf_) {}
+    Mat &operator=(const Mat &m)
+    {
+        rows = m.rows; cols = m.cols; data = m.data; step = m.step; type_ = m.type_; buf_ = m.buf_;
+        return *this;
+    }
     Mat(int r, int c, int type) { create(r, c, type); }
+    // header over caller-owned memory (CustomQDataStream.h:70 reads RAW mats this way, then clones)
+    Mat(int r, int c, int type, void *external) : rows(r), cols(c), data(static_cast<unsigned char *>(external)), type_(type)
+    {
+        step.v = (size_t)c * elemSize();
+    }
     Mat(int r, int c, int type, const Scalar &s)
     {
         create(r, c, type);
@@ -130,7 +151,8 @@ public:
     int depth() const { return CV_MAT_DEPTH(type_); }
     int channels() const { return CV_MAT_CN(type_); }
     size_t elemSize() const { return (size_t)(depth() == CV_8U ? 1 : 4) * channels(); }
-    Size size() const { return Size(cols, rows); }
+    unsigned char *ptr(int row = 0) { return data + (size_t)row * step.v; }
+    const unsigned char *ptr(int row = 0) const { return data + (size_t)row * step.v; }
     template <typename T> T *ptr(int row = 0) { return reinterpret_cast<T *>(data + (size_t)row * step.v); }
     template <typename T> const T *ptr(int row = 0) const { return reinterpret_cast<const T *>(data + (size_t)row * step.v); }
     Mat operator()(const Range &rowRange, const Range &colRange) const { return Mat(*this, rowRange, colRange); }
@@ -200,6 +222,49 @@ enum InterpolationFlags { INTER_CUBIC = 2, INTER_AREA = 3 };
 // OpenCV arithmetic: evaluated by the real OpenCV through the callback the harness installs (oracle/ref_generator_harness.cpp)
 void cvtColor(const Mat &src, Mat &dst, int code);
 void resize(const Mat &src, Mat &dst, Size dsize, double fx = 0, double fy = 0, int interpolation = 1);
+// PNG container of .mcs / .mil (CustomQDataStream.h:38-41, 76-81): the real OpenCV codec through the harness callback
+enum ImreadModes { IMREAD_UNCHANGED = -1 };
+bool imencode(const std::string &ext, const Mat &img, std::vector<uchar> &buf);
+Mat imdecode(const std::vector<uchar> &buf, int flags);
+// the 8U helpers CellShape.cpp uses on masks: binary threshold, flips, inequality + sum (operator==)
+enum ThresholdTypes { THRESH_BINARY = 0 };
+inline double threshold(const Mat &src, Mat &dst, double thresh, double maxval, int)
+{
+    Mat out(src.rows, src.cols, src.type());
+    for (int y = 0; y < src.rows; ++y)
+        for (size_t x = 0; x < (size_t)src.cols * src.elemSize(); ++x)
+            out.ptr<unsigned char>(y)[x] = src.ptr<unsigned char>(y)[x] > thresh ? (unsigned char)maxval : 0;
+    dst = out;
+    return thresh;
+}
+inline void flip(const Mat &src, Mat &dst, int flipCode)  // 0: around the x axis (rows), > 0: around the y axis, < 0: both
+{
+    Mat out(src.rows, src.cols, src.type());
+    const size_t es = src.elemSize();
+    for (int y = 0; y < src.rows; ++y)
+        for (int x = 0; x < src.cols; ++x) {
+            const int sy = flipCode <= 0 ? src.rows - 1 - y : y, sx = flipCode != 0 ? src.cols - 1 - x : x;
+            std::memcpy(out.ptr<unsigned char>(y) + x * es, src.ptr<unsigned char>(sy) + sx * es, es);
+        }
+    dst = out;
+}
+inline Mat operator!=(const Mat &a, const Mat &b)
+{
+    Mat out(a.rows, a.cols, CV_MAKETYPE(CV_8U, a.channels()));
+    for (int y = 0; y < a.rows; ++y)
+        for (size_t x = 0; x < (size_t)a.cols * a.elemSize(); ++x)
+            out.ptr<unsigned char>(y)[x] = a.ptr<unsigned char>(y)[x] != b.ptr<unsigned char>(y)[x] ? 255 : 0;
+    return out;
+}
+inline Scalar sum(const Mat &m)
+{
+    Scalar s;
+    const int cn = m.channels();
+    for (int y = 0; y < m.rows; ++y)
+        for (int x = 0; x < m.cols * cn; ++x)
+            s.val[x % cn] += m.ptr<unsigned char>(y)[x];
+    return s;
+}
 // 8U element-wise logic (buildPhotomosaic's coverage masks)
 inline void bitwise_or(const Mat &a, const Mat &b, Mat &dst)
 {

@@ -24,12 +24,12 @@ def run(oracle, backend, main, lib, group, grid_states, diff, scheme, rr, ra, ba
     oracle._ref()  # installs the OpenCV callbacks in libref_core.so (the same loaded instance libdropin_b200.so links to)
     from oracle.oracle import _group_args
     L = ctypes.CDLL(SO)
-    vp, i, dbl, lng = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_long
-    L.dropin_run.argtypes = [i, i, vp, i, i, lng, vp, i, i, i, vp, vp, vp, vp, dbl, i, i, i, i, vp, vp, vp, vp, vp, vp]
+    vp, i, lng = ctypes.c_void_p, ctypes.c_int, ctypes.c_long
+    L.dropin_run.argtypes = [i, i, vp, i, i, lng, vp, i, i, vp, vp, i, i, i, i, i, i, i, vp, vp, vp, vp, vp]
     main = np.ascontiguousarray(main, np.uint8)
     lib = np.ascontiguousarray(lib, np.uint8)
-    n, keep, shapes, masks, ds, dmasks = _group_args(group)
-    assert n == len(grid_states)
+    keep, shape, mask, pct, steps = _group_args(group)
+    n = len(grid_states)
     grids = [np.ascontiguousarray(g, np.int64).copy() for g in grid_states]
     rows = (ctypes.c_int * n)(*[g.shape[0] for g in grids])
     cols = (ctypes.c_int * n)(*[g.shape[1] for g in grids])
@@ -37,8 +37,8 @@ def run(oracle, backend, main, lib, group, grid_states, diff, scheme, rr, ra, ba
     bg = (ctypes.c_double * 4)(*[float(v) for v in background])
     mosaic = np.zeros(main.shape[:2] + (4,), np.uint8) if want_mosaic else None
     rc = L.dropin_run(backend, device, main.ctypes.data, main.shape[0], main.shape[1], main.strides[0], lib.ctypes.data, lib.shape[0],
-                      lib.shape[1], n, shapes, masks, ds, dmasks, float(group.detail), int(diff), int(scheme), int(rr), int(ra),
-                      rows, cols, gp, bg, None if mosaic is None else mosaic.ctypes.data, None)
+                      lib.shape[1], shape, mask, pct, steps, int(diff), int(scheme), int(rr), int(ra), n, rows, cols, gp, bg,
+                      None if mosaic is None else mosaic.ctypes.data)
     if rc < 0:
         raise RuntimeError("dropin_run failed (%d)" % rc)
     return rc, grids, mosaic

@@ -244,3 +244,28 @@ def test_hue_rotation_matches_opencv(L, rot):
     out = np.empty_like(img)
     assert L.mosaic_kernel_hue_rotate(0, img.ctypes.data, img.shape[0], img.shape[1], rot, out.ctypes.data) == 0
     assert np.array_equal(out, want), int((out != want).sum())
+
+
+def test_image_library_against_reference_object_code(oracle):
+    """The GPU ingest (ImageLibrary mirror -> mosaic_library_ingest) against the reference's OWN ImageLibrary.cpp object code
+    (oracle/_ref/libref_core.so, prebuilt): same images for tall / wide / square / smaller / equal-size inputs, and after
+    setImageSize."""
+    if not oracle.reference_generator_available():
+        pytest.skip("oracle/_ref/libref_core.so (reference object code) not present / not loadable")
+    from mosaicmagnifique_b200 import ImageLibrary
+    rng = np.random.default_rng(31)
+    ours, theirs = ImageLibrary(64, seed=2), oracle.ReferenceImageLibrary(64)
+    for i, (r, c) in enumerate([(300, 200), (256, 512), (40, 60), (64, 64), (97, 97), (513, 400), (31, 90)]):
+        im = rng.integers(0, 256, (r, c, 3), dtype=np.uint8)
+        ours.addImage(im, "im%d" % i)
+        theirs.add_image(im, "im%d" % i)
+    want = dict(theirs.items())
+    assert sorted(ours.getNames()) == sorted(want)
+    for name, img in zip(ours.getNames(), ours.getImages()):
+        assert np.array_equal(img, want[name]), name
+    ours.setImageSize(40)
+    theirs.set_image_size(40)
+    want = dict(theirs.items())
+    for name, img in zip(ours.getNames(), ours.getImages()):
+        assert np.array_equal(img, want[name]), name
+    theirs.close()

@@ -1,0 +1,192 @@
+"""CellShape / CellGroup / ImageLibrary and the .mcs / .mil containers, pinned on the reference's own object code:
+src/CellShape/CellShape.cpp, CellGroup.cpp, src/ImageLibrary/ImageLibrary.cpp and src/Other/CustomQDataStream.h are compiled
+unmodified into oracle/_ref/libref_core.so (Qt = the stand-ins of oracle/shim/qt_standins.h, OpenCV resize / PNG codec = cv2
+through callbacks). Checked against them: the oracle (CellShape.resized, CellGroup.make, load_mcs), the product's Python
+mirror and readers / writers (mosaicmagnifique_b200.CellShape.resized, formats.py), and the ingest procedure the GPU tests
+use as their expectation."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+CELLS = "/root/reference/Cells"
+FIELDS = ("row_spacing", "col_spacing", "alt_row_spacing", "alt_col_spacing", "alt_row_offset", "alt_col_offset",
+          "alt_col_flip_h", "alt_col_flip_v", "alt_row_flip_h", "alt_row_flip_v")
+
+
+@pytest.fixture(scope="module")
+def ref(oracle):
+    if not oracle.reference_generator_available():
+        pytest.skip("oracle/_ref/libref_core.so (reference object code) is not built")
+    return oracle
+
+
+def _shapes(o):
+    from mosaicmagnifique_b200 import synthetic
+    tri = o.CellShape.from_mask(synthetic.triangle_mask(64))
+    tri.row_spacing = tri.alt_row_spacing = 64
+    tri.col_spacing = tri.alt_col_spacing = 32
+    tri.alt_col_flip_v = True
+    tri.alt_row_flip_h = True
+    hx = o.CellShape.from_mask(synthetic.hexagon_mask(128))
+    hx.row_spacing = hx.alt_row_spacing = 96
+    hx.col_spacing = hx.alt_col_spacing = 110
+    hx.alt_row_offset = 55
+    hx.alt_col_offset = 3
+    return [o.CellShape.square(64), tri, hx]
+
+
+def _same_shape(a, b):
+    return a.size == b.size and np.array_equal(a.mask, b.mask) and all(getattr(a, f) == getattr(b, f) for f in FIELDS)
+
+
+def test_cell_shape_resized_matches_reference_object_code(ref):
+    """CellShape::resized (CellShape.cpp:281-312), shrinking (INTER_AREA) and growing (INTER_CUBIC): oracle and the product's
+    Python mirror against the reference's code, masks for all four flips included."""
+    from mosaicmagnifique_b200 import CellShape as ProductShape
+    for sh in _shapes(ref):
+        for new in (sh.size, sh.size // 2, 25, 37, sh.size + 19, 2 * sh.size):
+            want, m4 = ref.reference_cell_shape_resized(sh, new)
+            got = sh.resized(new)
+            assert _same_shape(got, want), (sh.size, new)
+            assert np.array_equal(got.masks4(), m4)
+            ps = ProductShape(sh.mask)
+            ps.rowSpacing, ps.colSpacing = sh.row_spacing, sh.col_spacing
+            ps.alternateRowSpacing, ps.alternateColSpacing = sh.alt_row_spacing, sh.alt_col_spacing
+            ps.alternateRowOffset, ps.alternateColOffset = sh.alt_row_offset, sh.alt_col_offset
+            pr = ps.resized(new)
+            assert np.array_equal(pr.getCellMask(), want.mask)
+            assert (pr.rowSpacing, pr.colSpacing, pr.alternateRowSpacing, pr.alternateColSpacing, pr.alternateRowOffset,
+                    pr.alternateColOffset) == (want.row_spacing, want.col_spacing, want.alt_row_spacing, want.alt_col_spacing,
+                                               want.alt_row_offset, want.alt_col_offset)
+
+
+@pytest.mark.parametrize("detail,steps", [(100, 0), (50, 2), (33, 1), (20, 3), (3, 1)])
+def test_cell_group_matches_reference_object_code(ref, detail, steps):
+    """CellGroup::setCellShape / setDetail / setSizeSteps (CellGroup.cpp:29-128): every step's normal and detail cell."""
+    for sh in _shapes(ref):
+        group = ref.CellGroup.make(sh, detail, steps)
+        for s in range(steps + 1):
+            for is_detail, mine in ((False, group.cells[s]), (True, group.detail_cells[s])):
+                want, m4 = ref.reference_cell_group_cell(group, s, is_detail)
+                assert _same_shape(mine, want), (sh.size, detail, s, is_detail)
+                assert np.array_equal(mine.masks4(), m4)
+
+
+def test_product_group_matches_reference_object_code(ref):
+    """The product's host model (csrc/host_model.cpp Group::build, through mosaic_host_grid_state's step sizes) is already
+    tested against the oracle; here its per-step grid geometry is tied to the reference's CellGroup via the grid sizes."""
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(260, 390, 5, block=32)
+    for sh in _shapes(ref):
+        group = ref.CellGroup.make(sh, 50, 2)
+        want = ref.reference_grid_state(group, main)
+        got = ref.grid_state(group, main)
+        assert [g.shape for g in got] == [g.shape for g in want]
+
+
+@pytest.mark.skipif(not os.path.isdir(CELLS), reason="reference Cells/*.mcs not present")
+def test_mcs_files_of_the_reference(ref, tmp_path):
+    """Every Cells/*.mcs of the reference: the reference's own loadFromFile vs the product reader (formats.load_mcs) and the
+    oracle reader; then both writers round-trip through the other side's reader."""
+    from mosaicmagnifique_b200 import formats
+    files = sorted(glob.glob(os.path.join(CELLS, "*.mcs")))
+    assert len(files) >= 10
+    for path in files:
+        want, m4 = ref.reference_load_mcs(path)
+        f = formats.load_mcs(path)
+        assert f["name"] == want.name
+        assert np.array_equal(f["mask"], want.mask)
+        assert all(f[k] == getattr(want, k) for k in FIELDS), path
+        o = ref.load_mcs(path)
+        assert _same_shape(o, want) and np.array_equal(o.masks4(), m4)
+        # product writer -> reference reader
+        p1 = str(tmp_path / "product.mcs")
+        formats.save_mcs(p1, f)
+        back, _ = ref.reference_load_mcs(p1)
+        assert _same_shape(back, want) and back.name == want.name
+        # reference writer -> product reader
+        p2 = str(tmp_path / "reference.mcs")
+        ref.reference_save_mcs(p2, want, want.name)
+        f2 = formats.load_mcs(p2)
+        assert f2["name"] == want.name and np.array_equal(f2["mask"], want.mask) and all(f2[k] == f[k] for k in FIELDS)
+
+
+def test_mcs_rejections_match(ref, tmp_path):
+    from mosaicmagnifique_b200 import formats
+    bad = str(tmp_path / "bad.mcs")
+    open(bad, "wb").write(b"\\x00\\x01\\x02\\x03" * 8)
+    with pytest.raises(ValueError):
+        ref.reference_load_mcs(bad)
+    with pytest.raises(ValueError):
+        formats.load_mcs(bad)
+
+
+def _procedure(o, im, size):
+    """What tests/test_gpu_kernels.py expects of mosaic_library_ingest: centre crop + resizeImage EXACT."""
+    r, c = im.shape[:2]
+    if c < r:
+        d = (r - c) // 2
+        im = im[d:c + d, :c]
+    elif c > r:
+        d = (c - r) // 2
+        im = im[:r, d:r + d]
+    return o.resize_image_exact(np.ascontiguousarray(im), size, size)
+
+
+def test_image_library_add_and_resize_match_reference_object_code(ref):
+    """ImageLibrary::addImage / setImageSize (ImageLibrary.cpp:42-86) from the reference's code: the crop + resize procedure
+    the GPU ingest is checked against IS what the reference computes (tall, wide, square, smaller and equal-size inputs)."""
+    rng = np.random.default_rng(21)
+    lib = ref.ReferenceImageLibrary(48)
+    srcs = {}
+    for i, (r, c) in enumerate([(100, 80), (48, 48), (30, 45), (200, 200), (97, 41), (64, 129)]):
+        im = rng.integers(0, 256, (r, c, 3), dtype=np.uint8)
+        srcs["im%d" % i] = im
+        lib.add_image(im, "im%d" % i)
+    items = lib.items()
+    assert sorted(n for n, _ in items) == sorted(srcs)  # inserted at random indices (std::random_device)
+    for name, img in items:
+        assert np.array_equal(img, _procedure(ref, srcs[name], 48)), name
+    before = dict(items)
+    lib.set_image_size(32)  # batchResizeMat on the stored (already 48 px) images
+    for name, img in lib.items():
+        assert np.array_equal(img, ref.resize_image_exact(before[name], 32, 32)), name
+    with pytest.raises(ValueError):
+        lib.add_image(np.zeros((0, 0, 3), np.uint8))
+    lib.close()
+
+
+def test_mil_container_round_trips_with_reference_object_code(ref, tmp_path):
+    """.mil (ImageLibrary.cpp:117-236): reference writer -> product reader, product writer -> reference reader, and the
+    product's ImageLibrary mirror on a reference-written file."""
+    from mosaicmagnifique_b200 import ImageLibrary, formats
+    rng = np.random.default_rng(22)
+    lib = ref.ReferenceImageLibrary(24)
+    for i in range(7):
+        lib.add_image(rng.integers(0, 256, (24, 24, 3), dtype=np.uint8), "image \\u00e9 %d" % i)  # non-ASCII name: UTF-16 on the wire
+    p1 = str(tmp_path / "reference.mil")
+    lib.save(p1)
+    items = lib.items()
+    images, names, size = formats.load_mil(p1)
+    assert size == 24 and names == [n for n, _ in items]
+    assert all(np.array_equal(a, b) for a, (_, b) in zip(images, items))
+    mirror = ImageLibrary(1)
+    mirror.loadFromFile(p1)
+    assert mirror.getImageSize() == 24 and mirror.getNames() == names and np.array_equal(mirror.asArray(), images)
+    p2 = str(tmp_path / "product.mil")
+    formats.save_mil(p2, images, names)
+    lib2 = ref.ReferenceImageLibrary(99)
+    lib2.load(p2)
+    assert lib2.image_size() == 24
+    got = lib2.items()
+    assert [n for n, _ in got] == names and all(np.array_equal(a, b) for a, (_, b) in zip(images, got))
+    bad = str(tmp_path / "bad.mil")
+    open(bad, "wb").write(b"\\x00" * 32)
+    with pytest.raises(ValueError):
+        lib2.load(bad)
+    with pytest.raises(ValueError):
+        formats.load_mil(bad)
+    lib.close()
+    lib2.close()
