@@ -578,15 +578,14 @@ def generate(main_bgr8: np.ndarray, lib_bgr8: np.ndarray, group: CellGroup, grid
 # ----------------------------------------------------------------------------- the reference's own generator object code
 #
 # oracle/_ref/libref_core.so holds the reference's PhotomosaicGeneratorBase.cpp, CPUPhotomosaicGenerator.cpp, GridGenerator.cpp,
-# ColourDifference.cpp, GridUtility.cpp, GridBounds.cpp, CellShape.cpp, CellGroup.cpp and ImageLibrary.cpp compiled UNMODIFIED (oracle/Makefile, stand-in headers oracle/shim,
-# harness oracle/ref_generator_harness.cpp). OpenCV arithmetic inside them (cvtColor, resize) and the colour-scheme variants
-# are answered by the callbacks below with the real OpenCV (cv2). Everything else -- setters, preprocessing flow, getCellAt,
+# ColourDifference.cpp, ColourScheme.cpp, GridUtility.cpp, GridBounds.cpp, CellShape.cpp, CellGroup.cpp and ImageLibrary.cpp
+# compiled UNMODIFIED (oracle/Makefile, stand-in headers oracle/shim,
+# harness oracle/ref_generator_harness.cpp). OpenCV arithmetic inside them (cvtColor, resize, the PNG codec) is answered by
+# the callbacks below with the real OpenCV (cv2). Everything else -- setters, preprocessing flow, getCellAt,
 # the best-fit loops, repeats, argmin, buildPhotomosaic, getGridState -- runs from the reference's object code.
 
 _CV_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                           ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long)
-_SCHEME_CB = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int, ctypes.c_int, ctypes.c_long,
-                              ctypes.POINTER(ctypes.c_uint8))
 _CODEC_CB = ctypes.CFUNCTYPE(ctypes.c_long, ctypes.c_int, ctypes.POINTER(ctypes.c_uint8), ctypes.c_long, ctypes.c_int, ctypes.c_int,
                              ctypes.c_int, ctypes.c_long, ctypes.POINTER(ctypes.c_uint8), ctypes.POINTER(ctypes.c_int))
 _ref_lib = None
@@ -622,20 +621,6 @@ def _cv_callback(op, code, src_p, rows, cols, cv_type, step, dst_p, drows, dcols
         draw[:] = out.view(np.uint8).reshape(drows, -1)
         return 0
     except Exception:  # noqa: BLE001 -- must not propagate through the C frames
-        import traceback
-        traceback.print_exc()
-        return 1
-
-
-def _scheme_callback(scheme, src_p, rows, cols, step, dst_p):
-    try:
-        raw, _, _ = _np_view(src_p, rows, cols, 16, step)  # 16 = CV_8UC3
-        img = np.ascontiguousarray(raw).reshape(rows, cols, 3)
-        variants = colour_scheme_variants(img, scheme)[1:]
-        dst = np.ctypeslib.as_array(dst_p, shape=(len(variants) * rows * cols * 3,))
-        dst[:] = np.concatenate([np.ascontiguousarray(v, np.uint8).reshape(-1) for v in variants]) if variants else dst
-        return 0
-    except Exception:  # noqa: BLE001
         import traceback
         traceback.print_exc()
         return 1
@@ -687,7 +672,8 @@ def _ref():
     if _ref_lib is None:
         R = ctypes.CDLL(os.path.join(HERE, "_ref", "libref_core.so"))
         vp, i, dbl, lng = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_long
-        R.ref_set_callbacks.argtypes = [_CV_CB, _SCHEME_CB, _CODEC_CB]
+        R.ref_set_callbacks.argtypes = [_CV_CB, _CODEC_CB]
+        R.ref_colour_scheme_variants.argtypes = [i, vp, i, i, lng, vp, i]
         R.ref_session_create.restype = vp
         R.ref_session_create.argtypes = [vp, i, i, lng, vp, i, i, vp, vp, i, i, i, i, i, i]
         R.ref_session_destroy.argtypes = [vp]
@@ -712,7 +698,7 @@ def _ref():
         R.ref_library_remove.argtypes = [vp, lng]
         R.ref_library_save.argtypes = [vp, ctypes.c_char_p]
         R.ref_library_load.argtypes = [vp, ctypes.c_char_p]
-        _ref_callbacks = (_CV_CB(_cv_callback), _SCHEME_CB(_scheme_callback), _CODEC_CB(_codec_callback))
+        _ref_callbacks = (_CV_CB(_cv_callback), _CODEC_CB(_codec_callback))
         R.ref_set_callbacks(*_ref_callbacks)
         _ref_lib = R
     return _ref_lib
@@ -821,6 +807,17 @@ def reference_grid_state(group: CellGroup, main_bgr: np.ndarray | None, height: 
         res.append(out[off:off + rows[s] * cols[s]].reshape(rows[s], cols[s]).copy())
         off += rows[s] * cols[s]
     return res
+
+
+def reference_colour_scheme_variants(img_bgr8: np.ndarray, scheme: int) -> list:
+    """ColourScheme::getFunction(scheme)(image) from the reference's own ColourScheme.cpp (hue rotations in float HSV_FULL; the
+    two cvtColor calls per variant are the real OpenCV)."""
+    img = np.ascontiguousarray(img_bgr8, np.uint8)
+    out = np.empty((4,) + img.shape, np.uint8)
+    v = _ref().ref_colour_scheme_variants(int(scheme), img.ctypes.data, img.shape[0], img.shape[1], img.strides[0], out.ctypes.data, 4)
+    if v < 0:
+        raise RuntimeError("reference colour scheme failed")
+    return [out[i].copy() for i in range(v)]
 
 
 def _describe_out(size_hint: int):

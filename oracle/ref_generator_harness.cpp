@@ -6,12 +6,13 @@
 //                                  getMaxProgress (PhotomosaicGeneratorBase.cpp:33-329)
 //   CPUPhotomosaicGenerator.cpp    generateBestFits, findCellBestFit, calculateRepeats (:33-225)
 //   GridGenerator.cpp              getGridState, findCellState (:29-193)
+//   ColourScheme.cpp               the colour-scheme variants (hue rotations in float HSV_FULL, :20-177)
 //   ColourDifference.cpp, GridUtility.cpp, GridBounds.cpp
 // What is NOT reference code here, and why:
 //   * cv::cvtColor / cv::resize are OpenCV arithmetic: forwarded through a callback to the real OpenCV (cv2, oracle.py);
-//   * ImageUtility.cpp (Qt GUI types, CUDA warping) and ColourScheme.cpp (cv::Mat_ / forEach templates) cannot be compiled
-//     against the stand-ins: the five ImageUtility functions the generator calls are restated below line by line, and the
-//     colour-scheme variants come from the oracle's cv2 restatement through a second callback;
+//   * ImageUtility.cpp (QPixmap / QProgressBar, feature detectors, CUDA warping) cannot be compiled against the stand-ins: the
+//     functions the other files call are restated below line by line; MatUtility.h's parallel visitors (OpenCV internals) are
+//     plain loops in the stand-in of the same name -- the functors they run are ColourScheme.cpp's own;
 //   * cv::imencode / cv::imdecode (the PNG payload of .mcs / .mil) are the real OpenCV codec through a third callback.
 // Also reference object code in the library: CellShape.cpp, CellGroup.cpp (per-step cell derivation, .mcs load / save through
 // the reference's CustomQDataStream.h) and ImageLibrary.cpp (addImage, setImageSize, .mil load / save), on the Qt stand-ins of
@@ -30,10 +31,7 @@ int g_ref_message_boxes = 0;
 //   op 0: cvtColor(code); op 1: resize(interpolation = code). dst is allocated by the caller side here.
 typedef int (*ref_cv_fn)(int op, int code, const unsigned char *src, int rows, int cols, int type, long step, unsigned char *dst,
                          int drows, int dcols, int dtype, long dstep);
-//   colour-scheme variants 1 .. V-1 of an 8U BGR image (variant 0 is the image itself), written back to back into dst
-typedef int (*ref_scheme_fn)(int scheme, const unsigned char *src, int rows, int cols, long step, unsigned char *dst);
 static ref_cv_fn g_cv = nullptr;
-static ref_scheme_fn g_scheme = nullptr;
 static std::vector<int> g_progress;
 
 static void call_cv(int op, int code, const cv::Mat &src, cv::Mat &dst, int drows, int dcols, int dtype)
@@ -182,27 +180,6 @@ double ImageUtility::calculateEntropy(const cv::Mat &t_in, const cv::Mat &t_mask
     return entropy;
 }
 
-// ---- ColourScheme::getFunction (ColourScheme.cpp:20-33): variants from the oracle's cv2 restatement
-ColourScheme::FunctionType ColourScheme::getFunction(const Type &t_type)
-{
-    const int scheme = static_cast<int>(t_type);
-    static const int kVariants[] = {1, 2, 3, 3, 4, 4};  // NONE, COMPLEMENTARY, TRIADIC, COMPOUND, TETRADIC, ANALAGOUS
-    if (scheme < 0 || scheme > 5)
-        throw std::invalid_argument("No function for given type");
-    return [scheme](const cv::Mat &t_image) {
-        std::vector<cv::Mat> out{t_image};  // the original image is always the first variant
-        const int extra = kVariants[scheme] - 1;
-        if (extra > 0) {
-            cv::Mat all(t_image.rows * extra, t_image.cols, t_image.type());
-            if (!g_scheme || g_scheme(scheme, t_image.data, t_image.rows, t_image.cols, (long)(size_t)t_image.step, all.data) != 0)
-                throw std::runtime_error("colour-scheme callback failed");
-            for (int v = 0; v < extra; ++v)
-                out.push_back(cv::Mat(all, cv::Range(v * t_image.rows, (v + 1) * t_image.rows), cv::Range(0, t_image.cols)).clone());
-        }
-        return out;
-    };
-}
-
 // ---- the moc-generated signal body
 void PhotomosaicGeneratorBase::progress(const int t_progressStep) { g_progress.push_back(t_progressStep); }
 
@@ -220,11 +197,26 @@ struct Session {
 }  // namespace
 
 extern "C" {
-void ref_set_callbacks(ref_cv_fn cv_cb, ref_scheme_fn scheme_cb, ref_codec_fn codec_cb)
+void ref_set_callbacks(ref_cv_fn cv_cb, ref_codec_fn codec_cb)
 {
     g_cv = cv_cb;
-    g_scheme = scheme_cb;
     g_codec = codec_cb;
+}
+
+// ColourScheme::getFunction(type)(image) (ColourScheme.cpp:20-177): the V variants of an 8U BGR image, written back to back into
+// out (capacity in images). Returns V, -3 on an exception.
+int ref_colour_scheme_variants(int scheme, const unsigned char *bgr, int rows, int cols, long stride, unsigned char *out, int capacity)
+{
+    try {
+        const std::vector<cv::Mat> v =
+            ColourScheme::getFunction(static_cast<ColourScheme::Type>(scheme))(ref_mat_from(bgr, rows, cols, CV_8UC3, (size_t)stride));
+        for (size_t i = 0; i < v.size() && (int)i < capacity; ++i)
+            for (int y = 0; y < rows; ++y)
+                std::memcpy(out + (i * rows + y) * (size_t)cols * 3, v[i].ptr<unsigned char>(y), (size_t)cols * 3);
+        return (int)v.size();
+    } catch (const std::exception &) {
+        return -3;
+    }
 }
 
 // A generator object configured like MainWindow.cpp:584-607 / tst_Generator.h:111-136 does it.

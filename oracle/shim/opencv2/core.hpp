@@ -28,6 +28,7 @@ template <typename T, int N> struct Vec {
 typedef Vec<double, 3> Vec3d;
 typedef Vec<float, 3> Vec3f;
 struct Point { int x = 0, y = 0; };
+struct Point3f { float x = 0, y = 0, z = 0; };
 struct Rect {
     int x = 0, y = 0, width = 0, height = 0;
     Rect() {}
@@ -173,20 +174,38 @@ public:
     void copyTo(Mat &&dst) const { copy_impl(dst, nullptr); }
     void copyTo(Mat &dst, const Mat &mask) const { copy_impl(dst, &mask); }
     void copyTo(Mat &&dst, const Mat &mask) const { copy_impl(dst, &mask); }
-    // convertTo: 8U -> 32F (dst = float(src) * float(alpha) + float(beta), the arithmetic of OpenCV's cvtScale for this pair)
+    // convertTo between 8U and 32F with OpenCV's arithmetic for these pairs: to 32F dst = float(src) * float(alpha) + float(beta);
+    // to 8U saturate_cast<uchar> = round half to even, then clamp (alpha / beta only ever 1 / 0 on that side here)
     void convertTo(Mat &dst, int rtype, double alpha = 1, double beta = 0) const
     {
-        if (depth() != CV_8U || CV_MAT_DEPTH(rtype) != CV_32F)
-            throw std::invalid_argument("shim convertTo: only 8U -> 32F");
-        Mat out(rows, cols, CV_MAKETYPE(CV_32F, channels()));
+        const int ddepth = CV_MAT_DEPTH(rtype);
+        if ((depth() != CV_8U && depth() != CV_32F) || (ddepth != CV_8U && ddepth != CV_32F))
+            throw std::invalid_argument("shim convertTo: only 8U / 32F");
+        Mat out(rows, cols, CV_MAKETYPE(ddepth, channels()));
         const float a = (float)alpha, b = (float)beta;
-        for (int y = 0; y < rows; ++y) {
-            const unsigned char *s = ptr<unsigned char>(y);
-            float *d = out.ptr<float>(y);
-            for (int x = 0; x < cols * channels(); ++x)
-                d[x] = (float)s[x] * a + b;
-        }
+        const bool scale = alpha != 1 || beta != 0;
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols * channels(); ++x) {
+                float v = depth() == CV_8U ? (float)ptr<unsigned char>(y)[x] : ptr<float>(y)[x];
+                if (scale)
+                    v = v * a + b;
+                if (ddepth == CV_32F)
+                    out.ptr<float>(y)[x] = v;
+                else {
+                    const long r = std::lrint(v);  // default rounding mode: to nearest, ties to even
+                    out.ptr<unsigned char>(y)[x] = (unsigned char)(r < 0 ? 0 : r > 255 ? 255 : r);
+                }
+            }
         dst = out;
+    }
+    // element-wise visitor (ColourScheme.cpp:49: forEach<cv::Point3f>)
+    template <typename T, typename F> void forEach(const F &op)
+    {
+        for (int y = 0; y < rows; ++y)
+            for (int x = 0; x < cols; ++x) {
+                const int pos[2] = {y, x};
+                op(ptr<T>(y)[x], pos);
+            }
     }
 
 private:
@@ -214,6 +233,26 @@ private:
     }
     int type_ = 0;
     std::shared_ptr<unsigned char> buf_;
+};
+
+// Typed header (ColourScheme.cpp uses cv::Mat_<cv::Point3f>): constructing it from a Mat of another element type converts,
+// like OpenCV's Mat_(const Mat&) does through convertTo
+template <typename T> struct DataTypeOf;
+template <> struct DataTypeOf<Point3f> { enum { type = CV_32FC3 }; };
+template <typename T> class Mat_ : public Mat {
+public:
+    Mat_() {}
+    Mat_(int r, int c) : Mat(r, c, DataTypeOf<T>::type) {}
+    Mat_(const Mat &m)
+    {
+        if (m.type() == DataTypeOf<T>::type)
+            Mat::operator=(m);
+        else {
+            Mat tmp;
+            m.convertTo(tmp, DataTypeOf<T>::type);
+            Mat::operator=(tmp);
+        }
+    }
 };
 
 // conversion / interpolation codes: the public values of the OpenCV API, handed unchanged to cv2 by the callback

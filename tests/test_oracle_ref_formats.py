@@ -190,3 +190,16 @@ def test_mil_container_round_trips_with_reference_object_code(ref, tmp_path):
         formats.load_mil(bad)
     lib.close()
     lib2.close()
+
+
+@pytest.mark.parametrize("scheme", [0, 1, 2, 3, 4, 5])
+def test_colour_scheme_variants_match_reference_object_code(ref, scheme):
+    """ColourScheme.cpp:36-177 compiled unmodified: number of variants, their order and every byte of every variant equal the
+    oracle's cv2 restatement (the product's hue_rotate kernel is checked against the same cv2 steps on the GPU)."""
+    from mosaicmagnifique_b200 import synthetic
+    img = synthetic.make_main_image(70, 93, 40 + scheme, block=16)  # odd width: exercises OpenCV's SIMD row tails
+    want = ref.reference_colour_scheme_variants(img, scheme)
+    got = ref.colour_scheme_variants(img, scheme)
+    assert len(got) == len(want) == {0: 1, 1: 2, 2: 3, 3: 3, 4: 4, 5: 4}[scheme]
+    for a, b in zip(got, want):
+        assert np.array_equal(np.asarray(a), b)
