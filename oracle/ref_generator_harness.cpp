@@ -6,13 +6,16 @@
 //                                  getMaxProgress (PhotomosaicGeneratorBase.cpp:33-329)
 //   CPUPhotomosaicGenerator.cpp    generateBestFits, findCellBestFit, calculateRepeats (:33-225)
 //   GridGenerator.cpp              getGridState, findCellState (:29-193)
+//   ImageUtility.cpp               resizeImage, batchResizeMat, imageToSquare, addAlphaChannel, calculateEntropy, edgeDetect ...
 //   ColourScheme.cpp               the colour-scheme variants (hue rotations in float HSV_FULL, :20-177)
 //   ColourDifference.cpp, GridUtility.cpp, GridBounds.cpp
 // What is NOT reference code here, and why:
 //   * cv::cvtColor / cv::resize are OpenCV arithmetic: forwarded through a callback to the real OpenCV (cv2, oracle.py);
-//   * ImageUtility.cpp (QPixmap / QProgressBar, feature detectors, CUDA warping) cannot be compiled against the stand-ins: the
-//     functions the other files call are restated below line by line; MatUtility.h's parallel visitors (OpenCV internals) are
-//     plain loops in the stand-in of the same name -- the functors they run are ColourScheme.cpp's own;
+//   * MatUtility.h's parallel visitors (built on OpenCV internals: ParallelLoopBody, n-dimensional indexing) are plain loops in
+//     the stand-in of the same name -- the functors they run are ColourScheme.cpp's own;
+//   * the 8U helpers of the stand-in cv namespace (threshold, flip, split / merge, copyMakeBorder, bitwise ops) are written
+//     out in oracle/shim/opencv2/core.hpp; the GUI-only ones (filter2D / dilate for the edge overlay) are simple versions, the
+//     feature / face detectors refuse to run;
 //   * cv::imencode / cv::imdecode (the PNG payload of .mcs / .mil) are the real OpenCV codec through a third callback.
 // Also reference object code in the library: CellShape.cpp, CellGroup.cpp (per-step cell derivation, .mcs load / save through
 // the reference's CustomQDataStream.h) and ImageLibrary.cpp (addImage, setImageSize, .mil load / save), on the Qt stand-ins of
@@ -47,7 +50,7 @@ void cv::cvtColor(const cv::Mat &src, cv::Mat &dst, int code)
     int dtype = src.type();
     if (code == cv::COLOR_BGR2GRAY)
         dtype = CV_MAKETYPE(src.depth(), 1);
-    else if (code == cv::COLOR_BGR2BGRA)
+    else if (code == cv::COLOR_BGR2BGRA || code == cv::COLOR_GRAY2RGBA)
         dtype = CV_MAKETYPE(src.depth(), 4);
     call_cv(0, code, src, dst, src.rows, src.cols, dtype);
 }
@@ -82,102 +85,6 @@ cv::Mat cv::imdecode(const std::vector<uchar> &buf, int)
     cv::Mat m(info[0], info[1], info[2]);
     g_codec(3, nullptr, 0, info[0], info[1], info[2], (long)(size_t)m.step, m.data, nullptr);
     return m;
-}
-
-// ---- ImageUtility, restated (the reference file cannot be compiled here, see the header comment)
-// ImageUtility.cpp:34-62
-cv::Mat ImageUtility::resizeImage(const cv::Mat &t_img, const int t_targetHeight, const int t_targetWidth, const ResizeType t_type)
-{
-    double resizeFactor = static_cast<double>(t_targetHeight) / t_img.rows;
-    if ((t_type == ResizeType::EXCLUSIVE && t_targetWidth < resizeFactor * t_img.cols) ||
-        (t_type == ResizeType::INCLUSIVE && t_targetWidth > resizeFactor * t_img.cols) ||
-        (t_type == ResizeType::EXACT && resizeFactor == 1.0))
-        resizeFactor = static_cast<double>(t_targetWidth) / t_img.cols;
-    if (resizeFactor == 1.0)
-        return t_img;  // the SAME Mat: with detail 100 % every colour-scheme variant of a cell keeps aliasing one buffer (Q1)
-    const cv::InterpolationFlags flags = (resizeFactor < 1) ? cv::INTER_AREA : cv::INTER_CUBIC;
-    cv::Mat result;
-    if (t_type == ResizeType::EXACT)
-        cv::resize(t_img, result, cv::Size(t_targetWidth, t_targetHeight), 0, 0, flags);
-    else
-        cv::resize(t_img, result, cv::Size((int)std::round(resizeFactor * t_img.cols), (int)std::round(resizeFactor * t_img.rows)), 0, 0,
-                   flags);
-    return result;
-}
-// ImageUtility.cpp:66-101
-bool ImageUtility::batchResizeMat(std::vector<cv::Mat> &t_images, const double t_ratio)
-{
-    if (t_images.empty())
-        return false;
-    const int h = (int)std::round(t_ratio * t_images.front().rows), w = (int)std::round(t_ratio * t_images.front().cols);
-    for (auto &im : t_images)
-        im = resizeImage(im, h, w, ResizeType::EXACT);
-    return true;
-}
-// ImageUtility.cpp:66-85 (the CPU branch)
-void ImageUtility::batchResizeMat(const std::vector<cv::Mat> &t_src, std::vector<cv::Mat> &t_dst, const int t_targetHeight,
-                                  const int t_targetWidth, const ResizeType t_type, QProgressBar *)
-{
-    t_dst.resize(t_src.size());
-    for (size_t i = 0; i < t_src.size(); ++i)
-        t_dst.at(i) = resizeImage(t_src.at(i), t_targetHeight, t_targetWidth, t_type);
-}
-// ImageUtility.cpp:249-276
-void ImageUtility::imageToSquare(cv::Mat &t_img, const SquareMethod t_method)
-{
-    if (t_img.cols == t_img.rows)
-        return;
-    if (t_method == SquareMethod::CROP) {
-        if (t_img.cols < t_img.rows) {
-            const int diff = (t_img.rows - t_img.cols) / 2;
-            t_img = t_img(cv::Range(diff, t_img.cols + diff), cv::Range(0, t_img.cols));
-        } else {
-            const int diff = (t_img.cols - t_img.rows) / 2;
-            t_img = t_img(cv::Range(0, t_img.rows), cv::Range(diff, t_img.rows + diff));
-        }
-    } else {  // PAD: copyMakeBorder(0, newSize - rows, 0, newSize - cols, BORDER_CONSTANT, 0)
-        const int newSize = std::max(t_img.cols, t_img.rows);
-        cv::Mat result = cv::Mat::zeros(newSize, newSize, t_img.type());
-        t_img.copyTo(result(cv::Rect(0, 0, t_img.cols, t_img.rows)));
-        t_img = result;
-    }
-}
-// GUI-only edge cells (CellGroup.cpp:33-48, 115-126): a plain copy stands in for the edge-detected, transparent overlay
-void ImageUtility::edgeDetect(const cv::Mat &t_src, cv::Mat &t_dst) { t_dst = t_src.clone(); }
-void ImageUtility::matMakeTransparent(const cv::Mat &t_src, cv::Mat &t_dst, const int) { t_dst = t_src.clone(); }
-// ImageUtility.cpp:173-186 (split + constant 255 plane + merge = BGR -> BGRA)
-void ImageUtility::addAlphaChannel(std::vector<cv::Mat> &t_images)
-{
-    for (auto &image : t_images)
-        cv::cvtColor(image, image, cv::COLOR_BGR2BGRA);
-}
-// ImageUtility.cpp:189-242
-double ImageUtility::calculateEntropy(const cv::Mat &t_in, const cv::Mat &t_mask)
-{
-    if (t_in.empty())
-        return 0;
-    if (!t_mask.empty() && (t_mask.rows != t_in.rows || t_mask.cols != t_in.cols || t_mask.channels() != 1))
-        return 0;
-    cv::Mat grayImage;
-    cv::cvtColor(t_in, grayImage, cv::COLOR_BGR2GRAY);
-    size_t pixelCount = 0;
-    std::vector<size_t> histogram(256, 0);
-    for (int row = 0; row < grayImage.rows; ++row) {
-        const uchar *p_im = grayImage.ptr<uchar>(row);
-        const uchar *p_mask = t_mask.empty() ? nullptr : t_mask.ptr<uchar>(row);
-        for (int col = 0; col < grayImage.cols; ++col)
-            if (!p_mask || p_mask[col] != 0) {
-                ++histogram.at(p_im[col]);
-                ++pixelCount;
-            }
-    }
-    double entropy = 0;
-    for (auto value : histogram) {
-        const double probability = value / static_cast<double>(pixelCount);
-        if (probability > 0)
-            entropy -= probability * std::log2(probability);
-    }
-    return entropy;
 }
 
 // ---- the moc-generated signal body

@@ -27,18 +27,44 @@ template <typename T, int N> struct Vec {
 };
 typedef Vec<double, 3> Vec3d;
 typedef Vec<float, 3> Vec3f;
-struct Point { int x = 0, y = 0; };
+typedef Vec<unsigned char, 4> Vec4b;
+struct Point {
+    int x = 0, y = 0;
+    Point() {}
+    Point(int x_, int y_) : x(x_), y(y_) {}
+};
+struct Point2f {
+    float x = 0, y = 0;
+    Point2f() {}
+    Point2f(float x_, float y_) : x(x_), y(y_) {}
+    Point2f &operator+=(const Point2f &o) { x += o.x; y += o.y; return *this; }
+};
 struct Point3f { float x = 0, y = 0, z = 0; };
+struct Size {
+    int width = 0, height = 0;
+    Size() {}
+    Size(int w, int h) : width(w), height(h) {}
+};
 struct Rect {
     int x = 0, y = 0, width = 0, height = 0;
     Rect() {}
     Rect(int x_, int y_, int w_, int h_) : x(x_), y(y_), width(w_), height(h_) {}
+    Rect(const Point &p, const Size &s) : x(p.x), y(p.y), width(s.width), height(s.height) {}
+    int area() const { return width * height; }
+    bool contains(const Point2f &p) const { return p.x >= x && p.x < x + width && p.y >= y && p.y < y + height; }
     Point tl() const { return {x, y}; }
     Point br() const { Point p; p.x = x + width; p.y = y + height; return p; }
     bool empty() const { return width <= 0 || height <= 0; }
 };
 // what GridBounds.cpp needs: equality and the bounding-box union (an empty operand contributes nothing)
 inline bool operator==(const Rect &a, const Rect &b) { return a.x == b.x && a.y == b.y && a.width == b.width && a.height == b.height; }
+inline Rect operator&(const Rect &a, const Rect &b)
+{
+    const int x1 = a.x > b.x ? a.x : b.x, y1 = a.y > b.y ? a.y : b.y;
+    const int x2 = a.x + a.width < b.x + b.width ? a.x + a.width : b.x + b.width;
+    const int y2 = a.y + a.height < b.y + b.height ? a.y + a.height : b.y + b.height;
+    return (x2 <= x1 || y2 <= y1) ? Rect() : Rect(x1, y1, x2 - x1, y2 - y1);
+}
 inline Rect operator|(const Rect &a, const Rect &b)
 {
     if (a.empty())
@@ -50,11 +76,6 @@ inline Rect operator|(const Rect &a, const Rect &b)
     const int y2 = a.y + a.height > b.y + b.height ? a.y + a.height : b.y + b.height;
     return Rect(x1, y1, x2 - x1, y2 - y1);
 }
-struct Size {
-    int width = 0, height = 0;
-    Size() {}
-    Size(int w, int h) : width(w), height(h) {}
-};
 struct Scalar {
     double val[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) : val{a, b, c, d} {}
@@ -77,6 +98,7 @@ struct Range {
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
 #define CV_8UC4 CV_MAKETYPE(CV_8U, 4)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
 
 namespace cv {
@@ -127,6 +149,7 @@ public:
                     ptr<float>(y)[x] = (float)v;
             }
     }
+    Mat(Size sz, int type, const Scalar &s) : Mat(sz.height, sz.width, type, s) {}
     Mat(const Mat &m, const Range &rowRange, const Range &colRange)
         : rows(rowRange.end - rowRange.start), cols(colRange.end - colRange.start),
           data(m.data ? m.data + (size_t)rowRange.start * m.step + (size_t)colRange.start * m.elemSize() : nullptr), step(m.step),
@@ -256,7 +279,7 @@ public:
 };
 
 // conversion / interpolation codes: the public values of the OpenCV API, handed unchanged to cv2 by the callback
-enum ColorConversionCodes { COLOR_BGR2BGRA = 0, COLOR_BGR2GRAY = 6, COLOR_BGR2Lab = 44, COLOR_BGR2HSV_FULL = 66, COLOR_HSV2BGR_FULL = 70 };
+enum ColorConversionCodes { COLOR_BGR2BGRA = 0, COLOR_BGR2GRAY = 6, COLOR_GRAY2RGBA = 9, COLOR_BGR2Lab = 44, COLOR_BGR2HSV_FULL = 66, COLOR_HSV2BGR_FULL = 70 };
 enum InterpolationFlags { INTER_CUBIC = 2, INTER_AREA = 3 };
 // OpenCV arithmetic: evaluated by the real OpenCV through the callback the harness installs (oracle/ref_generator_harness.cpp)
 void cvtColor(const Mat &src, Mat &dst, int code);
@@ -304,6 +327,93 @@ inline Scalar sum(const Mat &m)
             s.val[x % cn] += m.ptr<unsigned char>(y)[x];
     return s;
 }
+// ---- what else ImageUtility.cpp mentions. On the generator path: copyMakeBorder (imageToSquare PAD), split / merge
+// (addAlphaChannel). Off the path (GUI edge overlay, feature / face based cropping): simple or refusing stand-ins.
+enum BorderTypes { BORDER_CONSTANT = 0 };
+inline void copyMakeBorder(const Mat &src, Mat &dst, int top, int bottom, int left, int right, int, const Scalar &value = Scalar())
+{
+    Mat out(src.rows + top + bottom, src.cols + left + right, src.type(), value);
+    src.copyTo(out(Rect(left, top, src.cols, src.rows)));
+    dst = out;
+}
+inline void split(const Mat &m, std::vector<Mat> &channels)
+{
+    const int cn = m.channels();
+    channels.assign(cn, Mat());
+    for (int c = 0; c < cn; ++c) {
+        channels[c].create(m.rows, m.cols, CV_MAKETYPE(m.depth(), 1));
+        for (int y = 0; y < m.rows; ++y)
+            for (int x = 0; x < m.cols; ++x)
+                channels[c].ptr<unsigned char>(y)[x] = m.ptr<unsigned char>(y)[x * cn + c];
+    }
+}
+inline void merge(const std::vector<Mat> &channels, Mat &dst)
+{
+    const int cn = (int)channels.size();
+    Mat out(channels.at(0).rows, channels.at(0).cols, CV_MAKETYPE(channels.at(0).depth(), cn));
+    for (int c = 0; c < cn; ++c)
+        for (int y = 0; y < out.rows; ++y)
+            for (int x = 0; x < out.cols; ++x)
+                out.ptr<unsigned char>(y)[x * cn + c] = channels[c].ptr<unsigned char>(y)[x];
+    dst = out;
+}
+inline void bitwise_and(const Mat &a, const Mat &b, Mat &dst)
+{
+    Mat out(a.rows, a.cols, a.type());
+    for (int y = 0; y < a.rows; ++y)
+        for (size_t x = 0; x < (size_t)a.cols * a.elemSize(); ++x)
+            out.ptr<unsigned char>(y)[x] = a.ptr<unsigned char>(y)[x] & b.ptr<unsigned char>(y)[x];
+    dst = out;
+}
+// 8U single channel, small float kernel, zero border: enough for the 3 x 3 edge kernel of ImageUtility::edgeDetect
+inline void filter2D(const Mat &src, Mat &dst, int, const Mat &kernel, Point = Point(-1, -1), double delta = 0, int = BORDER_CONSTANT)
+{
+    Mat out(src.rows, src.cols, src.type());
+    const int kr = kernel.rows / 2, kc = kernel.cols / 2;
+    for (int y = 0; y < src.rows; ++y)
+        for (int x = 0; x < src.cols; ++x) {
+            double acc = delta;
+            for (int j = 0; j < kernel.rows; ++j)
+                for (int i = 0; i < kernel.cols; ++i) {
+                    const int sy = y + j - kr, sx = x + i - kc;
+                    if (sy >= 0 && sy < src.rows && sx >= 0 && sx < src.cols)
+                        acc += kernel.ptr<float>(j)[i] * src.ptr<unsigned char>(sy)[sx];
+                }
+            const long r = std::lrint(acc);
+            out.ptr<unsigned char>(y)[x] = (unsigned char)(r < 0 ? 0 : r > 255 ? 255 : r);
+        }
+    dst = out;
+}
+enum MorphShapes { MORPH_RECT = 0 };
+inline Mat getStructuringElement(int, Size ksize) { return Mat(ksize.height, ksize.width, CV_8UC1, Scalar(1)); }
+inline void dilate(const Mat &src, Mat &dst, const Mat &kernel)
+{
+    Mat out(src.rows, src.cols, src.type());
+    const int kr = kernel.rows / 2, kc = kernel.cols / 2;
+    for (int y = 0; y < src.rows; ++y)
+        for (int x = 0; x < src.cols; ++x) {
+            unsigned char m = 0;
+            for (int sy = std::max(0, y - kr); sy <= std::min(src.rows - 1, y + kr); ++sy)
+                for (int sx = std::max(0, x - kc); sx <= std::min(src.cols - 1, x + kc); ++sx)
+                    m = std::max(m, src.ptr<unsigned char>(sy)[sx]);
+            out.ptr<unsigned char>(y)[x] = m;
+        }
+    dst = out;
+}
+inline void equalizeHist(const Mat &, Mat &) { throw std::runtime_error("equalizeHist: not available in the checker"); }
+struct KeyPoint {
+    Point2f pt;
+};
+class FastFeatureDetector {
+public:
+    static std::shared_ptr<FastFeatureDetector> create() { return std::make_shared<FastFeatureDetector>(); }
+    void detect(const Mat &, std::vector<KeyPoint> &) { throw std::runtime_error("FastFeatureDetector: not available in the checker"); }
+};
+class CascadeClassifier {
+public:
+    bool empty() const { return true; }
+    void detectMultiScale(const Mat &, std::vector<Rect> &) { throw std::runtime_error("CascadeClassifier: not available in the checker"); }
+};
 // 8U element-wise logic (buildPhotomosaic's coverage masks)
 inline void bitwise_or(const Mat &a, const Mat &b, Mat &dst)
 {

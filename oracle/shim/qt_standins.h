@@ -214,7 +214,32 @@ inline QDataStream &operator>>(QDataStream &st, QByteArray &a)
     return st;
 }
 
-class QProgressBar;
+// qDebug(): a sink
+struct QDebugSink {
+    template <typename T> QDebugSink &operator<<(const T &) { return *this; }
+};
+inline QDebugSink qDebug() { return QDebugSink(); }
+
+// GUI types ImageUtility.h mentions (progress bar of batchResizeMat, pixmap conversion for previews): inert
+class QProgressBar {
+    int v_ = 0;
+public:
+    void setMaximum(int) {}
+    void setValue(int v) { v_ = v; }
+    int value() const { return v_; }
+    void setVisible(bool) {}
+};
+class QImage {
+public:
+    enum Format { Format_RGB888 = 13 };
+    QImage() {}
+    QImage(const unsigned char *, int, int, int, Format) {}
+    QImage rgbSwapped() const { return *this; }
+};
+class QPixmap {
+public:
+    static QPixmap fromImage(const QImage &) { return QPixmap(); }
+};
 
 class QObject {
 public:
