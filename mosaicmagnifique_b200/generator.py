@@ -151,10 +151,23 @@ class CellGroup:
     def getSizeSteps(self) -> int:
         return self._size_steps
 
+    def getCellSize(self, sizeStep: int = 0, detail: bool = False) -> int:
+        return self.getCell(sizeStep, detail).getSize()
+
     def getCell(self, sizeStep: int = 0, detail: bool = False) -> CellShape:
-        """Derived per-step cells, computed by the library (needs no GPU)."""
-        g = PhotomosaicGenerator._scratch_group(self)
-        return g.getCellGroupCell(sizeStep, detail)
+        """The normal or detail cell of one size step, derived as CellGroup::setDetail / setSizeSteps do (CellGroup.cpp:65-128):
+        every step halves the previous step's normal cell (integer division), the detail cell is the step's normal cell
+        resized to max(int(size * detail), 1). Host arithmetic of the library (CellShape.resized), no device needed."""
+        if self._shape is None:
+            raise ValueError("cell group has no shape")
+        if not 0 <= sizeStep <= self._size_steps:
+            raise IndexError("size step out of range")  # std::out_of_range from cells.at(), CellGroup.cpp:131-145
+        cell = self._shape
+        size = cell.getSize()
+        for _ in range(sizeStep):
+            size //= 2
+            cell = cell.resized(size)
+        return cell.resized(max(int(size * self.getDetail()), 1)) if detail else cell
 
 
 class PhotomosaicGenerator:
@@ -340,8 +353,3 @@ class PhotomosaicGenerator:
 
     def selectFromCandidates(self, step: int, scores_ptr: int, indices_ptr: int, k: int):
         self._ck(self._L.mosaic_select_from_candidates(self._h, step, scores_ptr, indices_ptr, k))
-
-    # ---- helper for CellGroup.getCell without a device: host model only
-    @staticmethod
-    def _scratch_group(cells: CellGroup):
-        raise MosaicError(-5, "CellGroup.getCell needs a generator: use PhotomosaicGenerator.getCellGroupCell after setCellGroup")

@@ -203,3 +203,36 @@ def test_colour_scheme_variants_match_reference_object_code(ref, scheme):
     assert len(got) == len(want) == {0: 1, 1: 2, 2: 3, 3: 3, 4: 4, 5: 4}[scheme]
     for a, b in zip(got, want):
         assert np.array_equal(np.asarray(a), b)
+
+
+@pytest.mark.parametrize("detail,steps", [(100, 0), (50, 2), (33, 1), (3, 1)])
+def test_product_cell_group_mirror_matches_reference_object_code(ref, detail, steps):
+    """mosaicmagnifique_b200.CellGroup.getCell (host arithmetic of libmosaic_b200.so) against the reference's CellGroup.cpp."""
+    from mosaicmagnifique_b200 import CellGroup, CellShape
+    for sh in _shapes(ref):
+        ps = CellShape(sh.mask)
+        ps.rowSpacing, ps.colSpacing = sh.row_spacing, sh.col_spacing
+        ps.alternateRowSpacing, ps.alternateColSpacing = sh.alt_row_spacing, sh.alt_col_spacing
+        ps.alternateRowOffset, ps.alternateColOffset = sh.alt_row_offset, sh.alt_col_offset
+        ps.alternateColFlipHorizontal, ps.alternateColFlipVertical = sh.alt_col_flip_h, sh.alt_col_flip_v
+        ps.alternateRowFlipHorizontal, ps.alternateRowFlipVertical = sh.alt_row_flip_h, sh.alt_row_flip_v
+        cg = CellGroup()
+        cg.setCellShape(ps)
+        cg.setDetail(detail)
+        cg.setSizeSteps(steps)
+        group = ref.CellGroup.make(sh, detail, steps)
+        for s in range(steps + 1):
+            for is_detail in (False, True):
+                want, m4 = ref.reference_cell_group_cell(group, s, is_detail)
+                got = cg.getCell(s, is_detail)
+                assert got.getSize() == want.size == cg.getCellSize(s, is_detail)
+                assert np.array_equal(got.getCellMask(), want.mask)
+                assert np.array_equal(got.getCellMask(True, False), m4[1]) and np.array_equal(got.getCellMask(False, True), m4[2])
+                assert (got.rowSpacing, got.colSpacing, got.alternateRowSpacing, got.alternateColSpacing, got.alternateRowOffset,
+                        got.alternateColOffset) == (want.row_spacing, want.col_spacing, want.alt_row_spacing,
+                                                    want.alt_col_spacing, want.alt_row_offset, want.alt_col_offset)
+                assert (got.alternateColFlipHorizontal, got.alternateColFlipVertical, got.alternateRowFlipHorizontal,
+                        got.alternateRowFlipVertical) == (want.alt_col_flip_h, want.alt_col_flip_v, want.alt_row_flip_h,
+                                                          want.alt_row_flip_v)
+        with pytest.raises(IndexError):
+            cg.getCell(steps + 1)
