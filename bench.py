@@ -173,8 +173,14 @@ def cpu_sample(cfg, main, lib, seconds):
         return r.nominal, r.visited, time.perf_counter()
 
     use_ref = oracle.reference_generator_available()
-
-    ref_gen = oracle.ReferenceGenerator(main, sub_lib, og, cfg["diff"], 0, cfg["rr"], cfg["ra"]) if use_ref else None
+    ref_gen = None
+    if use_ref:
+        try:  # a library built on another machine may not load / run here: fall back to the port and say so (kind = "port")
+            ref_gen = oracle.ReferenceGenerator(main, sub_lib, og, cfg["diff"], 0, cfg["rr"], cfg["ra"])
+            ref_gen.generate([np.full_like(state, -1)])
+        except Exception as e:  # noqa: BLE001
+            print("cpu baseline: reference object code unusable here (%s), timing the C port instead" % e, file=sys.stderr)
+            use_ref, ref_gen = False, None
 
     def timed(st):
         if use_ref:
