@@ -226,7 +226,8 @@ def test_cpp_mirror_compiles_and_links(tmp_path):
 @pytest.mark.parametrize("cell,detail,steps,shape_kind", [(64, 100, 2, "square"), (64, 50, 2, "square"), (48, 75, 1, "square"),
                                                            (64, 50, 1, "hex")])
 def test_host_grid_state_matches_oracle(L, oracle, cell, detail, steps, shape_kind):
-    """GridGenerator::getGridState incl. the entropy split and mergeBounds: library host model vs the cv2-based oracle."""
+    """GridGenerator::getGridState incl. the entropy split and mergeBounds: the library's host model vs the cv2-based oracle and,
+    when it is built, vs the reference's own object code."""
     pytest.importorskip("cv2")
     from mosaicmagnifique_b200 import synthetic
     from mosaicmagnifique_b200._capi import CellShapeC
@@ -240,6 +241,10 @@ def test_host_grid_state_matches_oracle(L, oracle, cell, detail, steps, shape_ki
     else:
         sh = oracle.CellShape.square(cell)
     want = oracle.grid_state(oracle.CellGroup.make(sh, detail, steps), main)
+    if oracle.reference_generator_available():
+        # ... and the reference's own GridGenerator.cpp / CellGroup.cpp object code (oracle/_ref/libref_core.so) says the same
+        ref_states = oracle.reference_grid_state(oracle.CellGroup.make(sh, detail, steps), main)
+        assert len(ref_states) == len(want) and all(np.array_equal(a, b) for a, b in zip(ref_states, want))
     c = CellShapeC(*sh.params())
     n_steps = ctypes.c_int()
     rows, cols = (ctypes.c_int * 8)(), (ctypes.c_int * 8)()
