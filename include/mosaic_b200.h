@@ -166,6 +166,21 @@ int mosaic_kernel_resize_area_u8(int device, const uint8_t *src, int64_t n, int 
 int mosaic_kernel_resize_area_f32(int device, const float *src, int64_t n, int size, int k, float *dst);
 int mosaic_kernel_resize_cubic_u8(int device, const uint8_t *src, int src_h, int src_w, int cn, uint8_t *dst, int dst_h, int dst_w);
 
+/* ---- on-disk containers of the reference (Qt-free, OpenCV-free: QDataStream layout and PNG codec inside the library).
+ * A file the reference would reject with std::invalid_argument gives MOSAIC_ERR_INVALID_ARGUMENT; mosaic_io_last_error() has
+ * the text (thread-local). Strings are UTF-8.
+ * .mcs = CellShape::loadFromFile / saveToFile (CellShape/CellShape.cpp:321-434): tiling parameters + the mask as stored.
+ *   mask_out may be NULL to query shape->size first; name_out may be NULL. */
+int mosaic_mcs_load(const char *path, mosaic_cell_shape *shape, uint8_t *mask_out, size_t mask_capacity, char *name_out,
+                    size_t name_capacity);
+int mosaic_mcs_save(const char *path, const mosaic_cell_shape *shape, const uint8_t *mask, const char *name_utf8);
+/* .mil = ImageLibrary::loadFromFile / saveToFile (ImageLibrary/ImageLibrary.cpp:117-236): n images of image_size^2 x 3 (BGR) and
+ * their names. mosaic_mil_info sizes the buffers (names_bytes = all names, each NUL-terminated, back to back). */
+int mosaic_mil_info(const char *path, int64_t *n_images, int *image_size, size_t *names_bytes);
+int mosaic_mil_load(const char *path, uint8_t *images_out, size_t images_capacity, char *names_out, size_t names_capacity);
+int mosaic_mil_save(const char *path, const uint8_t *images, int64_t n_images, int image_size, const char *names_nul_separated);
+const char *mosaic_io_last_error(void);
+
 /* ---- library ingest: ImageLibrary::addImage (ImageLibrary/ImageLibrary.cpp:62-86) minus the container bookkeeping.
  * Centre crop to a square (ImageUtility::imageToSquare CROP, Other/ImageUtility.cpp:249-267), then
  * ImageUtility::resizeImage EXACT to image_size (Other/ImageUtility.cpp:34-62: INTER_AREA when shrinking, INTER_CUBIC when

@@ -61,6 +61,28 @@ public:
     int getColSpacing() const { return m_c.col_spacing; }
     const std::vector<uint8_t> &getCellMask() const { return m_mask; }
     const mosaic_cell_shape &c() const { return m_c; }
+    void setName(const std::string &name) { m_name = name; }
+    const std::string &getName() const { return m_name; }
+
+    // CellShape::loadFromFile / saveToFile (.mcs, CellShape.cpp:321-434); std::invalid_argument like the reference
+    void loadFromFile(const std::string &filename)
+    {
+        mosaic_cell_shape c{};
+        char name[1024] = {0};
+        if (mosaic_mcs_load(filename.c_str(), &c, nullptr, 0, name, sizeof name) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_io_last_error());
+        std::vector<uint8_t> mask(static_cast<size_t>(c.size) * c.size);
+        if (mosaic_mcs_load(filename.c_str(), &c, mask.data(), mask.size(), nullptr, 0) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_io_last_error());
+        m_mask = std::move(mask);  // as stored: loadFromFile does not threshold (CellShape.cpp:405-410)
+        m_c = c;
+        m_name = name;
+    }
+    void saveToFile(const std::string &filename) const
+    {
+        if (mosaic_mcs_save(filename.c_str(), &m_c, m_mask.data(), m_name.c_str()) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_io_last_error());
+    }
 
 private:
     void init(int size)
@@ -71,6 +93,7 @@ private:
     }
     std::vector<uint8_t> m_mask;
     mosaic_cell_shape m_c{};
+    std::string m_name;
 };
 
 class CellGroup {
@@ -136,6 +159,41 @@ public:
         m_originalImages.clear();
         m_resizedImages.clear();
     }
+    // ImageLibrary::saveToFile / loadFromFile (.mil, ImageLibrary.cpp:117-236); std::invalid_argument like the reference
+    void saveToFile(const std::string &filename) const
+    {
+        const std::vector<uint8_t> all = packed();
+        std::string names;
+        for (const auto &n : m_names)
+            names.append(n).push_back('\0');
+        if (mosaic_mil_save(filename.c_str(), all.data(), static_cast<int64_t>(m_resizedImages.size()), static_cast<int>(m_imageSize),
+                            names.c_str()) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_io_last_error());
+    }
+    void loadFromFile(const std::string &filename)  // appends the file's images; its image size becomes the library's
+    {
+        int64_t n = 0;
+        int size = 0;
+        size_t nameBytes = 0;
+        if (mosaic_mil_info(filename.c_str(), &n, &size, &nameBytes) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_io_last_error());
+        std::vector<uint8_t> images(static_cast<size_t>(n) * size * size * 3);
+        std::vector<char> names(nameBytes + 1, 0);
+        if (mosaic_mil_load(filename.c_str(), images.data(), images.size(), names.data(), nameBytes) != MOSAIC_OK)
+            throw std::invalid_argument(mosaic_io_last_error());
+        m_imageSize = static_cast<size_t>(size);
+        const size_t per = static_cast<size_t>(size) * size * 3;
+        const char *p = names.data();
+        for (int64_t i = 0; i < n; ++i) {
+            m_names.emplace_back(p);
+            p += m_names.back().size() + 1;
+            std::vector<uint8_t> img(images.begin() + i * per, images.begin() + (i + 1) * per);
+            m_originalSize.push_back(size);
+            m_originalImages.push_back(img);
+            m_resizedImages.push_back(std::move(img));
+        }
+    }
+
     // contiguous [N][size][size][3] block for PhotomosaicGenerator::setLibrary
     std::vector<uint8_t> packed() const
     {

@@ -95,6 +95,12 @@ def capi():
         "mosaic_flip_at": (i, [shp, i, i]),
         "mosaic_host_grid_state": (i, [shp, vp, i, i, i, vp, i, i, sz, i, ip, ip, ip, vp, sz]),
         "mosaic_host_merge_bounds": (i, [vp, i, vp, i]),
+        "mosaic_mcs_load": (i, [c.c_char_p, shp, vp, sz, c.c_char_p, sz]),
+        "mosaic_mcs_save": (i, [c.c_char_p, shp, vp, c.c_char_p]),
+        "mosaic_mil_info": (i, [c.c_char_p, i64p, ip, c.POINTER(sz)]),
+        "mosaic_mil_load": (i, [c.c_char_p, vp, sz, c.c_char_p, sz]),
+        "mosaic_mil_save": (i, [c.c_char_p, vp, i64, i, c.c_char_p]),
+        "mosaic_io_last_error": (c.c_char_p, []),
         "mosaic_host_resize_area_u8": (i, [vp, i, i, i, vp, i, i]),
         "mosaic_host_resize_cubic_u8": (i, [vp, i, i, i, vp, i, i]),
         "mosaic_kernel_resize_cubic_u8": (i, [i, vp, i, i, i, vp, i, i]),

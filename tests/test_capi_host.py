@@ -223,6 +223,28 @@ def test_cpp_mirror_compiles_and_links(tmp_path):
     assert rc == (0 if torch.cuda.is_available() else 3)
 
 
+def test_cpp_mirror_container_methods(tmp_path):
+    """CellShape::loadFromFile / saveToFile of include/mosaic_b200.hpp (host only): write a .mcs with the Python writer, load and
+    re-save it through the C++ mirror, read the result back with the Python reader."""
+    import subprocess
+    from mosaicmagnifique_b200 import formats, synthetic
+    src, dst = str(tmp_path / "in.mcs"), str(tmp_path / "out.mcs")
+    fields = {"name": "hex \u00e4", "mask": synthetic.hexagon_mask(96), "row_spacing": 72, "col_spacing": 82, "alt_row_spacing": 72,
+              "alt_col_spacing": 82, "alt_row_offset": 41, "alt_col_offset": 0, "alt_col_flip_h": False, "alt_col_flip_v": True,
+              "alt_row_flip_h": False, "alt_row_flip_v": False}
+    formats.save_mcs(src, fields)
+    exe = str(tmp_path / "hpp_containers_check")
+    libdir = os.path.join(ROOT, "mosaicmagnifique_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-o", exe, os.path.join(ROOT, "tests", "helpers", "hpp_containers_check.cpp"),
+                           "-L" + libdir, "-lmosaic_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, src, dst, str(tmp_path / "missing.mcs")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[-3:] == ["96", "72", "82"]
+    back = formats.load_mcs(dst)
+    assert back["name"] == fields["name"] and np.array_equal(back["mask"], fields["mask"])
+    assert all(back[k] == fields[k] for k in fields if k not in ("name", "mask"))
+
+
 @pytest.mark.parametrize("cell,detail,steps,shape_kind", [(64, 100, 2, "square"), (64, 50, 2, "square"), (48, 75, 1, "square"),
                                                            (64, 50, 1, "hex")])
 def test_host_grid_state_matches_oracle(L, oracle, cell, detail, steps, shape_kind):

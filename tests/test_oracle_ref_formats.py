@@ -116,7 +116,7 @@ def test_mcs_files_of_the_reference(ref, tmp_path):
 def test_mcs_rejections_match(ref, tmp_path):
     from mosaicmagnifique_b200 import formats
     bad = str(tmp_path / "bad.mcs")
-    open(bad, "wb").write(b"\\x00\\x01\\x02\\x03" * 8)
+    open(bad, "wb").write(b"\x00\x01\x02\x03" * 8)
     with pytest.raises(ValueError):
         ref.reference_load_mcs(bad)
     with pytest.raises(ValueError):
@@ -165,7 +165,7 @@ def test_mil_container_round_trips_with_reference_object_code(ref, tmp_path):
     rng = np.random.default_rng(22)
     lib = ref.ReferenceImageLibrary(24)
     for i in range(7):
-        lib.add_image(rng.integers(0, 256, (24, 24, 3), dtype=np.uint8), "image \\u00e9 %d" % i)  # non-ASCII name: UTF-16 on the wire
+        lib.add_image(rng.integers(0, 256, (24, 24, 3), dtype=np.uint8), "image \u00e9 %d" % i)  # non-ASCII name: UTF-16 on the wire
     p1 = str(tmp_path / "reference.mil")
     lib.save(p1)
     items = lib.items()
@@ -183,7 +183,7 @@ def test_mil_container_round_trips_with_reference_object_code(ref, tmp_path):
     got = lib2.items()
     assert [n for n, _ in got] == names and all(np.array_equal(a, b) for a, (_, b) in zip(images, got))
     bad = str(tmp_path / "bad.mil")
-    open(bad, "wb").write(b"\\x00" * 32)
+    open(bad, "wb").write(b"\x00" * 32)
     with pytest.raises(ValueError):
         lib2.load(bad)
     with pytest.raises(ValueError):
@@ -236,3 +236,85 @@ def test_product_cell_group_mirror_matches_reference_object_code(ref, detail, st
                                                           want.alt_row_flip_v)
         with pytest.raises(IndexError):
             cg.getCell(steps + 1)
+
+
+# ---------------------------------------------------------------- the C ABI's own container readers / writers (csrc/containers.cpp)
+
+def _capi_mcs_load(L, path):
+    import ctypes
+    from mosaicmagnifique_b200._capi import CellShapeC
+    c = CellShapeC()
+    name = ctypes.create_string_buffer(512)
+    rc = L.mosaic_mcs_load(path.encode(), ctypes.byref(c), None, 0, name, 512)
+    if rc:
+        raise ValueError(L.mosaic_io_last_error().decode())
+    mask = np.empty((c.size, c.size), np.uint8)
+    assert L.mosaic_mcs_load(path.encode(), ctypes.byref(c), mask.ctypes.data, mask.size, name, 512) == 0
+    return c, mask, name.value.decode()
+
+
+@pytest.mark.skipif(not os.path.isdir(CELLS), reason="reference Cells/*.mcs not present")
+def test_capi_mcs_reader_and_writer_against_reference_object_code(ref, tmp_path):
+    """mosaic_mcs_load / mosaic_mcs_save (own QDataStream layout, own PNG codec incl. inflate) on every Cells/*.mcs of the
+    reference: equal to the reference's loadFromFile; the library's writer is read back by the reference."""
+    import ctypes
+    from mosaicmagnifique_b200 import capi
+    L = capi()
+    for path in sorted(glob.glob(os.path.join(CELLS, "*.mcs"))):
+        want, _ = ref.reference_load_mcs(path)
+        c, mask, name = _capi_mcs_load(L, path)
+        assert name == want.name and np.array_equal(mask, want.mask)
+        assert [c.size, c.row_spacing, c.col_spacing, c.alt_row_spacing, c.alt_col_spacing, c.alt_row_offset, c.alt_col_offset,
+                c.alt_col_flip_h, c.alt_col_flip_v, c.alt_row_flip_h, c.alt_row_flip_v] == [int(v) for v in want.params()]
+        out = str(tmp_path / "capi.mcs")
+        assert L.mosaic_mcs_save(out.encode(), ctypes.byref(c), mask.ctypes.data, name.encode()) == 0
+        back, _ = ref.reference_load_mcs(out)
+        assert _same_shape(back, want) and back.name == want.name
+    bad = str(tmp_path / "bad.mcs")
+    open(bad, "wb").write(b"\x00" * 40)
+    with pytest.raises(ValueError):
+        _capi_mcs_load(L, bad)
+    assert b".mcs" in L.mosaic_io_last_error()
+
+
+def test_capi_mil_reader_and_writer_against_reference_object_code(ref, tmp_path):
+    """mosaic_mil_info / _load / _save against the reference's own ImageLibrary::saveToFile / loadFromFile (cv2-compressed PNG
+    payloads in: dynamic-Huffman inflate; stored-block PNG out: decoded by the real codec on the reference side)."""
+    import ctypes
+    from mosaicmagnifique_b200 import capi, synthetic
+    L = capi()
+    lib = ref.ReferenceImageLibrary(40)
+    rng = np.random.default_rng(5)
+    smooth = synthetic.make_library(5, 40, 77)  # compressible: exercises back-references of the inflate
+    for i in range(5):
+        lib.add_image(smooth[i], "smooth %d" % i)
+    lib.add_image(rng.integers(0, 256, (40, 40, 3), dtype=np.uint8), "noise \u00fc")
+    p1 = str(tmp_path / "reference.mil")
+    lib.save(p1)
+    items = lib.items()
+    n, size, nb = ctypes.c_int64(), ctypes.c_int(), ctypes.c_size_t()
+    assert L.mosaic_mil_info(p1.encode(), ctypes.byref(n), ctypes.byref(size), ctypes.byref(nb)) == 0
+    assert (n.value, size.value) == (6, 40)
+    images = np.empty((6, 40, 40, 3), np.uint8)
+    names = ctypes.create_string_buffer(nb.value)
+    assert L.mosaic_mil_load(p1.encode(), images.ctypes.data, images.size, names, nb.value) == 0
+    got_names = names.raw[:nb.value].split(b"\x00")[:-1]
+    assert [g.decode() for g in got_names] == [nm for nm, _ in items]
+    assert all(np.array_equal(a, b) for a, (_, b) in zip(images, items))
+    # library writer -> reference reader
+    p2 = str(tmp_path / "capi.mil")
+    assert L.mosaic_mil_save(p2.encode(), images.ctypes.data, 6, 40, names.raw[:nb.value]) == 0
+    lib2 = ref.ReferenceImageLibrary(1)
+    lib2.load(p2)
+    got = lib2.items()
+    assert lib2.image_size() == 40 and [nm for nm, _ in got] == [nm for nm, _ in items]
+    assert all(np.array_equal(a, b) for a, (_, b) in zip(images, got))
+    # ... and the Python reader agrees with the C one
+    from mosaicmagnifique_b200 import formats
+    im2, nm2, sz2 = formats.load_mil(p2)
+    assert sz2 == 40 and nm2 == [nm for nm, _ in items] and np.array_equal(im2, images)
+    bad = str(tmp_path / "bad.mil")
+    open(bad, "wb").write(b"\x01" * 40)
+    assert L.mosaic_mil_info(bad.encode(), None, None, None) == -1
+    lib.close()
+    lib2.close()
