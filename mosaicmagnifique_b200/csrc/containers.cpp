@@ -11,6 +11,9 @@ namespace mm {
 
 namespace {
 
+constexpr uint32_t kMaxSide = 65536;            // images in these containers are cell masks and library tiles
+constexpr size_t kMaxInflated = (size_t)1 << 31;  // refuse to inflate more than 2 GiB from one stream
+
 // ------------------------------------------------------------------ checksums
 
 uint32_t crc32_of(const uint8_t *p, size_t n, uint32_t crc = 0)
@@ -126,6 +129,8 @@ bool inflate_codes(BitReader &br, const Huffman &lit, const Huffman &dist, std::
         const int sym = lit.decode(br);
         if (sym < 0)
             return false;
+        if (out.size() > kMaxInflated)
+            return false;
         if (sym < 256) {
             out.push_back((uint8_t)sym);
         } else if (sym == 256) {
@@ -161,7 +166,7 @@ bool inflate_raw(const uint8_t *data, size_t n, std::vector<uint8_t> &out)
                 return false;
             const uint32_t len = data[br.pos] | (data[br.pos + 1] << 8), nlen = data[br.pos + 2] | (data[br.pos + 3] << 8);
             br.pos += 4;
-            if ((len ^ 0xFFFFu) != nlen || br.pos + len > n)
+            if ((len ^ 0xFFFFu) != nlen || br.pos + len > n || out.size() > kMaxInflated)
                 return false;
             out.insert(out.end(), data + br.pos, data + br.pos + len);
             br.pos += len;
@@ -303,6 +308,10 @@ bool png_decode(const uint8_t *data, size_t n, Image8 &out, std::string &err)
     }
     if (interlace) {
         err = "interlaced PNG is not supported";
+        return false;
+    }
+    if (w > kMaxSide || h > kMaxSide) {  // keeps every size product below far from overflow
+        err = "PNG larger than 65536 pixels on a side";
         return false;
     }
     const int samples = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
@@ -491,7 +500,7 @@ struct Stream {
         const uint32_t type = u32(), rows = u32(), cols = u32();
         const std::vector<uint8_t> b = bytes();
         const uint32_t cn = ((type >> 3) & 511) + 1;
-        if (!ok || (type & 7) != 0 || b.size() != (size_t)rows * cols * cn) {
+        if (!ok || (type & 7) != 0 || rows > kMaxSide || cols > kMaxSide || b.size() != (size_t)rows * cols * cn) {
             err = "raw image in stream is not 8-bit or has the wrong size";
             return false;
         }

@@ -55,3 +55,56 @@ def test_reference_cell_fixtures(oracle):
         assert [f[k] for k in ("row_spacing", "col_spacing", "alt_row_spacing", "alt_col_spacing", "alt_row_offset", "alt_col_offset")] == o.params()[1:7]
     hexa = formats.load_mcs("/root/reference/Cells/Hexagon.mcs")
     assert (hexa["row_spacing"], hexa["col_spacing"], hexa["alt_row_offset"]) == (385, 440, 220)
+
+
+def test_container_readers_survive_corrupt_files(tmp_path):
+    """csrc/containers.cpp parses files from disk: truncated, bit-flipped and size-lying inputs must come back as an error (or a
+    successful parse), never as a crash or an unbounded allocation. Runs in a child process so that a crash is a test failure,
+    not the end of the test run."""
+    import subprocess
+    import sys
+    from mosaicmagnifique_b200 import formats, synthetic
+    good = str(tmp_path / "good.mcs")
+    formats.save_mcs(good, {"name": "t", "mask": synthetic.hexagon_mask(64), "row_spacing": 48, "col_spacing": 55, "alt_row_spacing": 48,
+                            "alt_col_spacing": 55, "alt_row_offset": 27, "alt_col_offset": 0, "alt_col_flip_h": False,
+                            "alt_col_flip_v": False, "alt_row_flip_h": True, "alt_row_flip_v": False})
+    mil = str(tmp_path / "good.mil")
+    formats.save_mil(mil, synthetic.make_library(3, 24, 5), ["a", "b", "c"])
+    script = r'''
+import ctypes, sys
+import numpy as np
+from mosaicmagnifique_b200 import capi
+from mosaicmagnifique_b200._capi import CellShapeC
+L = capi()
+rng = np.random.default_rng(123)
+outcomes = {0: 0, -1: 0}
+for path, is_mcs in ((sys.argv[1], True), (sys.argv[2], False)):
+    data = bytearray(open(path, "rb").read())
+    variants = [bytes(data[:n]) for n in range(0, len(data), max(1, len(data) // 60))]
+    for _ in range(300):
+        d = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+        variants.append(bytes(d))
+    lying = bytearray(data)            # IHDR claiming a gigantic image
+    i = bytes(lying).find(b"IHDR")
+    lying[i + 4:i + 12] = b"\xff\xff\xff\xff\xff\xff\xff\xff"
+    variants.append(bytes(lying))
+    for v in variants:
+        p = sys.argv[3]
+        open(p, "wb").write(v)
+        if is_mcs:
+            c = CellShapeC()
+            mask = np.zeros(1 << 16, np.uint8)
+            rc = L.mosaic_mcs_load(p.encode(), ctypes.byref(c), mask.ctypes.data, mask.size, None, 0)
+        else:
+            rc = L.mosaic_mil_info(p.encode(), None, None, None)
+        assert rc in (0, -1), rc
+        outcomes[rc] += 1
+print(outcomes[0], outcomes[-1])
+'''
+    out = subprocess.run([sys.executable, "-c", script, good, mil, str(tmp_path / "variant.bin")], capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stdout + out.stderr
+    ok, rejected = (int(v) for v in out.stdout.split())
+    assert rejected > 300  # nearly every corruption is caught (CRC / Adler / structure); the rest parse as valid files
