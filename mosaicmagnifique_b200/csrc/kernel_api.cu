@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -359,6 +360,17 @@ int io_fail(const std::string &err)
     g_io_error = err;
     return MOSAIC_ERR_INVALID_ARGUMENT;
 }
+// nothing may throw across the C ABI (a multi-gigabyte file can make a vector allocation fail)
+int io_guard(const std::function<int()> &body)
+{
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        return io_fail("out of host memory");
+    } catch (const std::exception &e) {
+        return io_fail(e.what());
+    }
+}
 void copy_text(const std::string &s, char *out, size_t cap)
 {
     if (!out || !cap)
@@ -374,102 +386,112 @@ const char *mosaic_io_last_error(void) { return g_io_error.c_str(); }
 int mosaic_mcs_load(const char *path, mosaic_cell_shape *shape, uint8_t *mask_out, size_t mask_capacity, char *name_out,
                     size_t name_capacity)
 {
-    if (!path || !shape)
-        return io_fail("null argument");
-    McsFile f;
-    std::string err;
-    if (!load_mcs(path, f, err))
-        return io_fail(err);
-    const Shape &s = f.shape;
-    *shape = mosaic_cell_shape{s.size, s.row_spacing, s.col_spacing, s.alt_row_spacing, s.alt_col_spacing, s.alt_row_offset,
-                               s.alt_col_offset, s.alt_col_flip_h, s.alt_col_flip_v, s.alt_row_flip_h, s.alt_row_flip_v};
-    if (mask_out) {
-        if (mask_capacity < s.mask.size())
-            return io_fail("mask buffer too small");
-        memcpy(mask_out, s.mask.data(), s.mask.size());
-    }
-    copy_text(f.name, name_out, name_capacity);
-    return MOSAIC_OK;
+    return io_guard([&]() -> int {
+        if (!path || !shape)
+            return io_fail("null argument");
+        McsFile f;
+        std::string err;
+        if (!load_mcs(path, f, err))
+            return io_fail(err);
+        const Shape &s = f.shape;
+        *shape = mosaic_cell_shape{s.size, s.row_spacing, s.col_spacing, s.alt_row_spacing, s.alt_col_spacing, s.alt_row_offset,
+                                   s.alt_col_offset, s.alt_col_flip_h, s.alt_col_flip_v, s.alt_row_flip_h, s.alt_row_flip_v};
+        if (mask_out) {
+            if (mask_capacity < s.mask.size())
+                return io_fail("mask buffer too small");
+            memcpy(mask_out, s.mask.data(), s.mask.size());
+        }
+        copy_text(f.name, name_out, name_capacity);
+        return MOSAIC_OK;
+    });
 }
 
 int mosaic_mcs_save(const char *path, const mosaic_cell_shape *shape, const uint8_t *mask, const char *name_utf8)
 {
-    if (!path || !shape || !mask || shape->size <= 0)
-        return io_fail("null argument");
-    McsFile f;
-    f.name = name_utf8 ? name_utf8 : "";
-    Shape &s = f.shape;
-    s.size = shape->size;
-    s.mask.assign(mask, mask + (size_t)shape->size * shape->size);
-    s.row_spacing = shape->row_spacing; s.col_spacing = shape->col_spacing;
-    s.alt_row_spacing = shape->alt_row_spacing; s.alt_col_spacing = shape->alt_col_spacing;
-    s.alt_row_offset = shape->alt_row_offset; s.alt_col_offset = shape->alt_col_offset;
-    s.alt_col_flip_h = shape->alt_col_flip_h != 0; s.alt_col_flip_v = shape->alt_col_flip_v != 0;
-    s.alt_row_flip_h = shape->alt_row_flip_h != 0; s.alt_row_flip_v = shape->alt_row_flip_v != 0;
-    std::string err;
-    return save_mcs(path, f, err) ? MOSAIC_OK : io_fail(err);
+    return io_guard([&]() -> int {
+        if (!path || !shape || !mask || shape->size <= 0)
+            return io_fail("null argument");
+        McsFile f;
+        f.name = name_utf8 ? name_utf8 : "";
+        Shape &s = f.shape;
+        s.size = shape->size;
+        s.mask.assign(mask, mask + (size_t)shape->size * shape->size);
+        s.row_spacing = shape->row_spacing; s.col_spacing = shape->col_spacing;
+        s.alt_row_spacing = shape->alt_row_spacing; s.alt_col_spacing = shape->alt_col_spacing;
+        s.alt_row_offset = shape->alt_row_offset; s.alt_col_offset = shape->alt_col_offset;
+        s.alt_col_flip_h = shape->alt_col_flip_h != 0; s.alt_col_flip_v = shape->alt_col_flip_v != 0;
+        s.alt_row_flip_h = shape->alt_row_flip_h != 0; s.alt_row_flip_v = shape->alt_row_flip_v != 0;
+        std::string err;
+        return save_mcs(path, f, err) ? MOSAIC_OK : io_fail(err);
+    });
 }
 
 int mosaic_mil_info(const char *path, int64_t *n_images, int *image_size, size_t *names_bytes)
 {
-    if (!path)
-        return io_fail("null argument");
-    MilFile f;
-    std::string err;
-    if (!load_mil(path, f, err))
-        return io_fail(err);
-    if (n_images)
-        *n_images = (int64_t)f.names.size();
-    if (image_size)
-        *image_size = f.image_size;
-    if (names_bytes) {
-        *names_bytes = 0;
-        for (const std::string &n : f.names)
-            *names_bytes += n.size() + 1;
-    }
-    return MOSAIC_OK;
+    return io_guard([&]() -> int {
+        if (!path)
+            return io_fail("null argument");
+        MilFile f;
+        std::string err;
+        if (!load_mil(path, f, err))
+            return io_fail(err);
+        if (n_images)
+            *n_images = (int64_t)f.names.size();
+        if (image_size)
+            *image_size = f.image_size;
+        if (names_bytes) {
+            *names_bytes = 0;
+            for (const std::string &n : f.names)
+                *names_bytes += n.size() + 1;
+        }
+        return MOSAIC_OK;
+    });
 }
 
 int mosaic_mil_load(const char *path, uint8_t *images_out, size_t images_capacity, char *names_out, size_t names_capacity)
 {
-    if (!path)
-        return io_fail("null argument");
-    MilFile f;
-    std::string err;
-    if (!load_mil(path, f, err))
-        return io_fail(err);
-    if (images_out) {
-        if (images_capacity < f.images.size())
-            return io_fail("image buffer too small");
-        memcpy(images_out, f.images.data(), f.images.size());
-    }
-    if (names_out) {
-        size_t off = 0;
-        for (const std::string &n : f.names) {
-            if (off + n.size() + 1 > names_capacity)
-                return io_fail("name buffer too small");
-            memcpy(names_out + off, n.c_str(), n.size() + 1);
-            off += n.size() + 1;
+    return io_guard([&]() -> int {
+        if (!path)
+            return io_fail("null argument");
+        MilFile f;
+        std::string err;
+        if (!load_mil(path, f, err))
+            return io_fail(err);
+        if (images_out) {
+            if (images_capacity < f.images.size())
+                return io_fail("image buffer too small");
+            memcpy(images_out, f.images.data(), f.images.size());
         }
-    }
-    return MOSAIC_OK;
+        if (names_out) {
+            size_t off = 0;
+            for (const std::string &n : f.names) {
+                if (off + n.size() + 1 > names_capacity)
+                    return io_fail("name buffer too small");
+                memcpy(names_out + off, n.c_str(), n.size() + 1);
+                off += n.size() + 1;
+            }
+        }
+        return MOSAIC_OK;
+    });
 }
 
 int mosaic_mil_save(const char *path, const uint8_t *images, int64_t n_images, int image_size, const char *names_nul_separated)
 {
-    if (!path || n_images < 0 || image_size < 0 || (n_images > 0 && !images))
-        return io_fail("null argument");
-    MilFile f;
-    f.image_size = image_size;
-    f.images.assign(images, images + (size_t)n_images * image_size * image_size * 3);
-    const char *p = names_nul_separated;
-    for (int64_t i = 0; i < n_images; ++i) {
-        f.names.push_back(p ? std::string(p) : std::string());
-        if (p)
-            p += f.names.back().size() + 1;
-    }
-    std::string err;
-    return save_mil(path, f, err) ? MOSAIC_OK : io_fail(err);
+    return io_guard([&]() -> int {
+        if (!path || n_images < 0 || image_size < 0 || (n_images > 0 && !images))
+            return io_fail("null argument");
+        MilFile f;
+        f.image_size = image_size;
+        f.images.assign(images, images + (size_t)n_images * image_size * image_size * 3);
+        const char *p = names_nul_separated;
+        for (int64_t i = 0; i < n_images; ++i) {
+            f.names.push_back(p ? std::string(p) : std::string());
+            if (p)
+                p += f.names.back().size() + 1;
+        }
+        std::string err;
+        return save_mil(path, f, err) ? MOSAIC_OK : io_fail(err);
+    });
 }
 
 int mosaic_host_merge_bounds(const int *rects_xywh, int n, int *out_xywh, int out_capacity)
