@@ -495,3 +495,26 @@ def test_config2_shape_against_reference_object_code(oracle):
     n, n_diff = _direct_reference_case(oracle, main, lib, hx.resized(128), 2, 50, 0, 2, 500)
     assert n > 60
     print("config 2 shape: %d of %d cells differ from the reference (tie band)" % (n_diff, n))
+
+
+@pytest.mark.skipif(not os.environ.get("MOSAIC_RANDOM_GPU"), reason="opt-in (MOSAIC_RANDOM_GPU=1): written after the round's GPU "
+                    "budget was spent, to be switched on once it has run on a B200")
+def test_randomised_configurations_cuda_vs_reference_object_code(oracle):
+    """GPU twin of tests/test_oracle_ref_generator.py::test_randomised_configurations_against_reference_object_code: the same
+    60 seeded random configurations through the CUDA path, against the reference's own object code."""
+    if not oracle.reference_generator_available():
+        pytest.skip("oracle/_ref/libref_core.so (reference object code) not present / not loadable")
+    from mosaicmagnifique_b200 import MosaicError
+    from tests.test_oracle_ref_generator import _random_config
+    rng = np.random.default_rng(20261017)
+    ran = unsupported = 0
+    for it in range(60):
+        c = _random_config(oracle, rng, it)
+        try:
+            _direct_reference_case(oracle, c["main"], c["lib"], c["shape"], c["diff"], c["detail"], c["steps"], c["rr"], c["ra"], c["scheme"])
+            ran += 1
+        except MosaicError as e:
+            if e.code != -5:  # MOSAIC_ERR_UNSUPPORTED: size disagreement between library and detail mask (SURVEY Q4)
+                raise
+            unsupported += 1
+    assert ran >= 40, (ran, unsupported)
