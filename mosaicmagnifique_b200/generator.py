@@ -115,16 +115,21 @@ class CellShape:
 
 
 def load_mcs(path: str) -> CellShape:
-    """Reads a .mcs cell shape (CellShape::loadFromFile, CellShape.cpp:363-434) through formats.load_mcs."""
-    from .formats import load_mcs as _load
-    f = _load(path)
-    s = CellShape(f["mask"])
-    s.rowSpacing, s.colSpacing = f["row_spacing"], f["col_spacing"]
-    s.alternateRowSpacing, s.alternateColSpacing = f["alt_row_spacing"], f["alt_col_spacing"]
-    s.alternateRowOffset, s.alternateColOffset = f["alt_row_offset"], f["alt_col_offset"]
-    s.alternateColFlipHorizontal, s.alternateColFlipVertical = f["alt_col_flip_h"], f["alt_col_flip_v"]
-    s.alternateRowFlipHorizontal, s.alternateRowFlipVertical = f["alt_row_flip_h"], f["alt_row_flip_v"]
-    s.name = f["name"]
+    """Reads a .mcs cell shape (CellShape::loadFromFile, CellShape.cpp:363-434) with the library's own reader
+    (mosaic_mcs_load: QDataStream layout + PNG codec in csrc/containers.cpp, no OpenCV / Qt involved)."""
+    L = capi()
+    c = CellShapeC()
+    name = ctypes.create_string_buffer(1024)
+    bpath = str(path).encode()
+    rc = L.mosaic_mcs_load(bpath, ctypes.byref(c), None, 0, name, len(name))
+    if rc:
+        raise MosaicError(rc, L.mosaic_io_last_error().decode())
+    mask = np.empty((c.size, c.size), np.uint8)
+    rc = L.mosaic_mcs_load(bpath, ctypes.byref(c), mask.ctypes.data, mask.size, name, len(name))
+    if rc:
+        raise MosaicError(rc, L.mosaic_io_last_error().decode())
+    s = CellShape._from_c(c, mask)
+    s.name = name.value.decode()
     return s
 
 

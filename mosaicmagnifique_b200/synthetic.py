@@ -68,3 +68,20 @@ def triangle_mask(size: int) -> np.ndarray:
     y, x = np.mgrid[0:size, 0:size].astype(np.float64)
     half = np.abs(x - (size - 1) / 2)
     return np.where(half <= (y + 1) / 2, 255, 0).astype(np.uint8)
+
+
+def make_photo_library(src: np.ndarray, n: int, size: int, seed: int = 2002) -> np.ndarray:
+    """n x size x size x 3 uint8 BGR library cut from a photograph: seeded square crops of side k * size (k = 1..6) at random
+    positions, reduced by the k x k block mean. Substitute for the reference's Library/lib.mil / big-lib.mil, which are missing
+    from its checkout ("build a deterministic one from tiles of the sample images")."""
+    rng = np.random.default_rng(seed)
+    h, w = src.shape[:2]
+    kmax = max(1, min(6, min(h, w) // size))
+    lib = np.empty((n, size, size, 3), np.uint8)
+    for i in range(n):
+        k = int(rng.integers(1, kmax + 1))
+        side = k * size
+        y, x = int(rng.integers(0, h - side + 1)), int(rng.integers(0, w - side + 1))
+        crop = src[y:y + side, x:x + side].astype(np.uint32).reshape(size, k, size, k, 3)
+        lib[i] = ((crop.sum((1, 3)) + (k * k) // 2) // (k * k)).astype(np.uint8)
+    return lib

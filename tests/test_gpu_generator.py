@@ -126,11 +126,10 @@ def test_size_steps_with_library_grid_state(oracle):
     assert total > 30
 
 
-def test_mcs_fixture_if_present(oracle):
-    """Cells/Hexagon.mcs of the reference checkout, when it is available (not on the GPU box)."""
-    path = "/root/reference/Cells/Hexagon.mcs"
-    if not os.path.exists(path):
-        pytest.skip("reference checkout not present")
+def test_mcs_fixture(oracle):
+    """Cells/Hexagon.mcs of the reference (committed under tests/golden/cells/), read by the checker's reader here; the product's
+    own reader and the remaining shapes are covered by tests/test_gpu_baseline_configs.py."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cells", "Hexagon.mcs")
     sh = oracle.load_mcs(path)
     main, lib = _inputs(61, 200, 260, 30, 64)
     _run_case(oracle, main, lib, sh.resized(64), 2, 50, 0, 1, 50)
@@ -497,24 +496,52 @@ def test_config2_shape_against_reference_object_code(oracle):
     print("config 2 shape: %d of %d cells differ from the reference (tie band)" % (n_diff, n))
 
 
-@pytest.mark.skipif(not os.environ.get("MOSAIC_RANDOM_GPU"), reason="opt-in (MOSAIC_RANDOM_GPU=1): written after the round's GPU "
-                    "budget was spent, to be switched on once it has run on a B200")
+def _q4_ok(group, n_states):
+    """the halved library must meet the detail mask size at every generated step, else the reference itself reads out
+    of range (and the engine answers MOSAIC_ERR_UNSUPPORTED)."""
+    lib_ds = group.detail_cells[0].size
+    for s in range(1, n_states):
+        lib_ds = int(round(0.5 * lib_ds))
+        if lib_ds != group.detail_cells[s].size:
+            return False
+    return True
+
+
 def test_randomised_configurations_cuda_vs_reference_object_code(oracle):
     """GPU twin of tests/test_oracle_ref_generator.py::test_randomised_configurations_against_reference_object_code: the same
-    60 seeded random configurations through the CUDA path, against the reference's own object code."""
+    60 seeded random configurations through the CUDA path, against the reference's own object code (the reference's
+    CPU-vs-CUDA differential matrix, test/tst_CUDAGenerator.h:226-823, at random instead of hand-picked points)."""
     if not oracle.reference_generator_available():
         pytest.skip("oracle/_ref/libref_core.so (reference object code) not present / not loadable")
-    from mosaicmagnifique_b200 import MosaicError
+    from mosaicmagnifique_b200 import CellGroup, MosaicError, PhotomosaicGenerator
     from tests.test_oracle_ref_generator import _random_config
     rng = np.random.default_rng(20261017)
-    ran = unsupported = 0
+    ran = unsupported = cells = differ = 0
     for it in range(60):
         c = _random_config(oracle, rng, it)
-        try:
-            _direct_reference_case(oracle, c["main"], c["lib"], c["shape"], c["diff"], c["detail"], c["steps"], c["rr"], c["ra"], c["scheme"])
-            ran += 1
-        except MosaicError as e:
-            if e.code != -5:  # MOSAIC_ERR_UNSUPPORTED: size disagreement between library and detail mask (SURVEY Q4)
-                raise
+        group = oracle.CellGroup.make(c["shape"], c["detail"], c["steps"])
+        if not _q4_ok(group, len(oracle.grid_state(group, c["main"]))):
+            # the engine must refuse exactly these (never a silent wrong answer)
+            gen = PhotomosaicGenerator(0)
+            gen.setMainImage(c["main"])
+            gen.setLibrary(c["lib"])
+            cg = CellGroup()
+            cg.setCellShape(_to_product_shape(c["shape"]))
+            cg.setDetail(c["detail"])
+            cg.setSizeSteps(c["steps"])
+            gen.setCellGroup(cg)
+            gen.computeGridState()
+            with pytest.raises(MosaicError) as e:
+                gen.generateBestFits()
+            assert e.value.code == -5
+            gen.close()
             unsupported += 1
+            continue
+        n, d = _direct_reference_case(oracle, c["main"], c["lib"], c["shape"], c["diff"], c["detail"], c["steps"], c["rr"], c["ra"],
+                                      c["scheme"])
+        ran += 1
+        cells += n
+        differ += d
+    print("randomised CUDA-vs-reference: %d configurations, %d cells, %d differ (all inside the tie band); %d configurations are "
+          "out-of-range reads in the reference and refused by the engine" % (ran, cells, differ, unsupported))
     assert ran >= 40, (ran, unsupported)
