@@ -1,22 +1,30 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the photomosaic best-fit path (BASELINE.json config 4).
+"""bench.py -- benchmark of the photomosaic best-fit path on the BASELINE.json configurations.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg4|cfg4-small|...]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload cfg4|cfg2|cfg3|cfg5|...] [--configs all|none]
 
-Workload (BASELINE.json configs[3], SURVEY.md section 8d "Config 4 (headline)"): synthetic 7680x4320 main image x
-10,000-image library of 128x128 tiles, CIEDE2000, square cells 128, detail 100 %, repeat range 8 / addition 500.
-A "step" is one complete generateBestFits(): preprocessing, the fused difference-sum kernel over cells x library,
-the repeat-penalised wavefront selection, grid back on the host. The same job is sharded by grid rows over N GPUs
-(strong scaling); under torchrun every rank is one process on one GPU.
+Headline workload (BASELINE.json configs[3], SURVEY.md section 8d "Config 4"): synthetic 7680x4320 main image x 10,000-image
+library of 128x128 tiles, CIEDE2000, square cells 128, detail 100 %, repeat range 8 / addition 500. A "step" is one complete
+generateBestFits(): preprocessing, the fused difference-sum kernel over cells x library, the repeat-penalised wavefront
+selection, grid back on the host. The same job is sharded over N GPUs (strong scaling); under torchrun every rank is one
+process on one GPU.
 
-value  : pixel-differences / second (active, in-bound mask pixels x library images; SURVEY.md 8d metric (i)) with the
-         8-bit inputs already resident in HBM when the timed region starts.
-e2e    : the same metric through the reference-shaped API from pinned HOST buffers each step: setMainImage + setLibrary
-         (H2D) + generateBestFits + getBestFits (D2H).
-The CPU oracle (and the reference's own generator compiled into oracle/_ref) is used here ONLY for the cpu_baseline leg
-and for --impl reference.
+value   : pixel-differences / second (active, in-bound mask pixels x library images; SURVEY.md 8d metric (i)) with the 8-bit inputs
+          already resident in HBM when the timed region starts.
+e2e     : the same metric through the reference-shaped API from pinned HOST buffers each step: setMainImage + setLibrary (H2D) +
+          generateBestFits + getBestFits (D2H).
+configs : the other GPU configurations of BASELINE.json AS SPECIFIED, each with value / e2e / kernel roofline / tie band:
+          cfg2 = SampleImages main image (tests/golden/images) x 2,000-image substitute library, CIEDE2000, Cells/Hexagon.mcs @128,
+          detail 50 %; cfg3 = 4K x 2,000, CIE76, 64 px cells, 3 size levels; cfg5 = 16K x 20,000, RGB Euclidean, Cells/Puzzle.mcs
+          @128, detail 50 %. Cell shapes are read and resized by the PRODUCT (mosaic_mcs_load, CellShape.resized).
+roofline: the binding EXECUTED pipe of the difference kernel (FP32 lane-ops or MUFU ops per pixel-difference counted from the
+          SASS of the shipped library -- profiles/r2_sass_counts.json, tools/sass_counts.py -- x units / CUDA-event duration,
+          against the pipe rates measured live by the in-library micro-benchmark).
+The CPU oracle package (the reference's own generator compiled into oracle/_ref) is imported ONLY by the cpu_baseline leg and
+by --impl reference; the B200 arm builds everything it needs with the product.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -30,34 +38,42 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# algorithmic work per pixel-difference of the REFERENCE formula
-WORK = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1}, 1: {"flop": 9, "sfu": 1}}
-# what this engine's kernel executes per pixel-difference (colour_math.cuh; instruction counts from SASS / ncu)
-EXECUTED = {2: {"mufu": 9, "fp32_lane_ops": 79}, 0: {"mufu": 1, "fp32_lane_ops": 7}, 1: {"mufu": 1, "fp32_lane_ops": 7}}
+CELLS_DIR = os.path.join(ROOT, "tests", "golden", "cells")
+SAMPLE_IMAGE = os.path.join(ROOT, "tests", "golden", "images", "edgar-perez-424673-unsplash.jpg")
+DIFF_NAMES = ["RGB_EUCLIDEAN", "CIE76", "CIEDE2000"]
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the difference kernel, per launch on 1 GPU, from the ncu captures committed
-# under profiles/ (cfg4: r1_diff_sum_ciede2000_v4_cfg4.txt, the shipped kernel; cfg5: r1_dram_traffic_cfg5_final.csv).
-# Not measurable inside an un-profiled run.
-NCU_TRAFFIC_BYTES = {"cfg4": 132214958000 + 197510656, "cfg5": 35904559360 + 13339392}
+# algorithmic work per pixel-difference of the REFERENCE formula (ColourDifference.cpp as written)
+WORK_REFERENCE_FORMULA = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1}, 1: {"flop": 9, "sfu": 1}}
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the difference kernel, per launch on 1 GPU, from the ncu --set full captures
+# committed under profiles/ (not measurable inside an un-profiled run): workload -> (bytes, file)
+NCU_TRAFFIC = {
+    "cfg4": (132214958000 + 197510656, "profiles/r1_diff_sum_ciede2000_v4_cfg4.txt"),
+}
 
 WORKLOADS = {
-    # name: (H, W, n_lib, cell, detail, diff, range, addition, seed)
     "cfg4": dict(h=4320, w=7680, n_lib=10000, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
                  desc="synthetic 8K (7680x4320) main x 10,000-image library, CIEDE2000, cell 128, detail 100%, repeat 8/500"),
-    "cfg4-d50": dict(h=4320, w=7680, n_lib=10000, cell=128, detail=50, diff=2, rr=8, ra=500, seed=1004,
-                     desc="config 4 at detail 50%"),
+    "cfg4-d50": dict(h=4320, w=7680, n_lib=10000, cell=128, detail=50, diff=2, rr=8, ra=500, seed=1004, desc="config 4 at detail 50%"),
     "cfg4-small": dict(h=1080, w=1920, n_lib=1000, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
                        desc="config 4 scaled down (1920x1080 x 1,000 images) for quick runs"),
     "cfg4-med": dict(h=2160, w=3840, n_lib=2500, cell=128, detail=100, diff=2, rr=8, ra=500, seed=1004,
                      desc="config 4 scaled down (3840x2160 x 2,500 images) for kernel tuning"),
-    "cfg2": dict(h=4000, w=5000, n_lib=2000, cell=128, detail=50, diff=2, rr=0, ra=0, seed=1002, shape="hexagon",
-                 desc="synthetic 5000x4000 main x 2,000-image library, CIEDE2000, Hexagon cell shape (Hexagon.mcs geometry, "
-                      "alternate-row flips, clipped edge cells), cell 128, detail 50%"),
+    "cfg2": dict(h=4000, w=5000, n_lib=2000, cell=128, detail=50, diff=2, rr=2, ra=500, seed=1002, shape="Hexagon", photo=True,
+                 desc="SampleImages/edgar-perez (5000x4000) main x 2,000-image library cut from it (big-lib.mil is absent from the "
+                      "reference checkout), CIEDE2000, Cells/Hexagon.mcs @128 (spacing 96/110, odd-row offset 55, clipped edge cells), "
+                      "detail 50%, repeat 2/500"),
     "cfg3": dict(h=2160, w=3840, n_lib=2000, cell=64, detail=100, diff=1, rr=0, ra=0, seed=1003, steps=2,
                  desc="synthetic 4K (3840x2160) main x 2,000-image library, CIE76, 64px cells, 3 size levels (entropy sub-cell split)"),
-    "cfg5": dict(h=8640, w=15360, n_lib=20000, cell=128, detail=50, diff=0, rr=0, ra=0, seed=1005,
-                 desc="synthetic 16K main x 20,000-image library, RGB Euclidean, square cells at detail 50%"),
+    "cfg5": dict(h=8640, w=15360, n_lib=20000, cell=128, detail=50, diff=0, rr=0, ra=0, seed=1005, shape="Puzzle",
+                 desc="synthetic 16K (15360x8640) main x 20,000-image library, RGB Euclidean, Cells/Puzzle.mcs @128 (spacing 108, "
+                      "72% active), detail 50%"),
+    "cfg5-square": dict(h=8640, w=15360, n_lib=20000, cell=128, detail=50, diff=0, rr=0, ra=0, seed=1005,
+                        desc="config 5 with square cells (round-1 shape of this workload; kernel comparison only)"),
+    "cfg5-small": dict(h=2160, w=3840, n_lib=4000, cell=128, detail=50, diff=0, rr=0, ra=0, seed=1005, shape="Puzzle",
+                       desc="config 5 scaled down (3840x2160 x 4,000 images) for quick runs"),
 }
+SECONDARY = ["cfg2", "cfg3", "cfg5"]
 
 
 def parse():
@@ -67,9 +83,53 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--configs", default="all", choices=["all", "none"],
+                    help="all: after the headline workload also run BASELINE configs 2, 3 and 5 (a few steps each) into the `configs` object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=45.0, help="target CPU time of the full-library cpu_baseline sample")
     return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- shared by both arms (no oracle, no GPU)
+
+def make_inputs(cfg, main_out=None, lib_out=None):
+    """Seeded inputs of a workload as numpy arrays (optionally written into caller-provided pinned buffers)."""
+    from mosaicmagnifique_b200 import synthetic
+    H, W, N, S = cfg["h"], cfg["w"], cfg["n_lib"], cfg["cell"]
+    if cfg.get("photo"):
+        import cv2  # JPEG decoding of the fixture only (the reference reads it with cv::imread as well)
+        main = cv2.imread(SAMPLE_IMAGE, cv2.IMREAD_COLOR)
+        assert main is not None and main.shape == (H, W, 3), "tests/golden/images fixture missing"
+        lib = synthetic.make_photo_library(main, N, S, cfg["seed"])
+    else:
+        main = synthetic.make_main_image(H, W, cfg["seed"] + 1000)
+        lib = synthetic.make_library(N, S, cfg["seed"], out=lib_out)
+    if main_out is not None:
+        main_out[...] = main
+        main = main_out
+    if lib_out is not None and lib is not lib_out:
+        lib_out[...] = lib
+        lib = lib_out
+    return main, lib
+
+
+def make_shape(cfg):
+    """The workload's top-level cell shape, built by the PRODUCT only: square cells, or a .mcs file of the reference read by
+    mosaic_mcs_load and resized to the cell size by the library's host model (CellShape::resized)."""
+    from mosaicmagnifique_b200 import CellShape, load_mcs
+    if cfg.get("shape"):
+        return load_mcs(os.path.join(CELLS_DIR, cfg["shape"] + ".mcs")).resized(cfg["cell"])
+    return CellShape(cfg["cell"])
+
+
+def describe(cfg, name, world):
+    """`config` of the JSON line: identical in both arms (static description of the workload)."""
+    return {"workload": cfg["desc"], "name": name, "main": [cfg["w"], cfg["h"]], "library": cfg["n_lib"], "cell": cfg["cell"],
+            "detail": cfg["detail"], "size_steps": cfg.get("steps", 0), "cell_shape": cfg.get("shape", "square"),
+            "colour_difference": DIFF_NAMES[cfg["diff"]], "repeat": [cfg["rr"], cfg["ra"]],
+            "cache": "packed library + cells of a step exceed the 126 MB L2 many times over; nothing is reused across steps",
+            "parallelism": ("valid cells (raster order) sharded over %d GPUs, library replicated, top-K candidates all-gathered (NCCL)" % world)
+            if world > 1 else "1 GPU"}
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -102,9 +162,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        num = lambda s: s.replace(".", "").isdigit()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and num(r[1])]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and num(r[2])]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and num(r[3])]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -116,142 +177,195 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# ----------------------------------------------------------------------------- CPU reference arm / baseline
+# ----------------------------------------------------------------------------- CPU reference arm / baseline (the ONLY oracle users)
 
-def make_shapes(cfg):
-    """(product CellShape, oracle CellShape) of a workload: square cells, or the reference's Hexagon.mcs geometry
-    (512 px mask, row spacing 385, column spacing 440, odd-row offset 220) resized to the cell size,
-    with alternate-row horizontal flips switched on so that flipped masks are exercised."""
-    from mosaicmagnifique_b200 import CellShape, synthetic
-    from oracle import oracle
-    if cfg.get("shape") == "hexagon":
-        o = oracle.CellShape.from_mask(synthetic.hexagon_mask(512))
-        o.row_spacing = o.alt_row_spacing = 385
-        o.col_spacing = o.alt_col_spacing = 440
-        o.alt_row_offset = 220
-        o.alt_row_flip_h = True
-        o = o.resized(cfg["cell"])
-    else:
-        o = oracle.CellShape.square(cfg["cell"])
-    p = CellShape(o.mask)
-    p.rowSpacing, p.colSpacing, p.alternateRowSpacing, p.alternateColSpacing = o.row_spacing, o.col_spacing, o.alt_row_spacing, o.alt_col_spacing
-    p.alternateRowOffset, p.alternateColOffset = o.alt_row_offset, o.alt_col_offset
-    p.alternateColFlipHorizontal, p.alternateColFlipVertical = o.alt_col_flip_h, o.alt_col_flip_v
-    p.alternateRowFlipHorizontal, p.alternateRowFlipVertical = o.alt_row_flip_h, o.alt_row_flip_v
-    return p, o
-
-
-def cpu_sample(cfg, main, lib, seconds):
-    """Times the reference's CPU generator on a bounded sample of the workload: the first grid row(s) x a library prefix,
-    1 thread (CPUPhotomosaicGenerator is single-threaded), f64, early exit on.
+class CpuReference:
+    """The reference's CPU generator on bounded samples of a workload, 1 thread (CPUPhotomosaicGenerator is single-threaded),
+    f64, early exit on.
     kind "reference": the reference's OWN PhotomosaicGeneratorBase.cpp / CPUPhotomosaicGenerator.cpp / ColourDifference.cpp /
-    GridUtility.cpp, compiled unmodified into oracle/_ref/libref_core.so (oracle/Makefile; the prebuilt library travels to
-    the GPU box); the timed call is its generateBestFits() -- preprocessing (OpenCV calls answered by cv2), getCellAt, the
-    best-fit loops -- on 8-bit inputs already handed to its setters.
-    kind "port": the plain-C restatement (oracle/mosaic_oracle.c), when that library is not there."""
-    from oracle import oracle
-    og = oracle.CellGroup.make(make_shapes(cfg)[1], cfg["detail"], 0)  # sample = the top size level
-    n_lib = min(len(lib), 64)
-    sub_lib = lib[:n_lib]
-    t0 = time.perf_counter()
-    state = oracle.grid_state(og, main)[0]
-    mains = [oracle.to_working_space(main, cfg["diff"])]
-    lib_f = oracle.preprocess_library(sub_lib, og, cfg["diff"])
-    prep_s = time.perf_counter() - t0
-    valid_rows = [y for y in range(state.shape[0]) if (state[y] >= 0).any()]
+    GridUtility.cpp, compiled unmodified into oracle/_ref/libref_core.so (oracle/Makefile; the prebuilt library travels to the GPU
+    box); a timed call is its setGridState + generateBestFits + getBestFits on 8-bit inputs already handed to its setters.
+    generateBestFits preprocesses the WHOLE main image and library on every call; at full size that is amortised over thousands
+    of cells, in a sample it is not, so it is measured with an empty grid state and subtracted (which only favours the CPU).
+    kind "port": the plain-C restatement (oracle/mosaic_oracle.c) when that library is absent or unusable."""
 
-    def first_rows(k):
-        st = np.full_like(state, -1)
-        for y in valid_rows[:k]:
-            st[y] = state[y]
+    def __init__(self, cfg, main, lib):
+        from oracle import oracle
+        self.o = oracle
+        self.cfg, self.main, self.lib = cfg, main, lib
+        shp = make_shape(cfg)  # product-side reading / resizing of the cell shape, handed to the checker as plain numbers
+        osh = oracle.CellShape.from_mask(shp.getCellMask())
+        osh.row_spacing, osh.col_spacing = shp.rowSpacing, shp.colSpacing
+        osh.alt_row_spacing, osh.alt_col_spacing = shp.alternateRowSpacing, shp.alternateColSpacing
+        osh.alt_row_offset, osh.alt_col_offset = shp.alternateRowOffset, shp.alternateColOffset
+        osh.alt_col_flip_h, osh.alt_col_flip_v = shp.alternateColFlipHorizontal, shp.alternateColFlipVertical
+        osh.alt_row_flip_h, osh.alt_row_flip_v = shp.alternateRowFlipHorizontal, shp.alternateRowFlipVertical
+        self.og = oracle.CellGroup.make(osh, cfg["detail"], 0)  # samples are taken on the top size level
+        self.state = oracle.grid_state(self.og, main)[0]
+        ys, xs = np.nonzero(self.state >= 0)
+        self.valid = list(zip(ys.tolist(), xs.tolist()))  # raster order
+        self.use_ref = oracle.reference_generator_available()
+        self._gens = {}
+
+    def _gen(self, n_lib):
+        """a reference generator object holding the first n_lib library images"""
+        if n_lib not in self._gens:
+            for g in self._gens.values():
+                g.close()
+            self._gens.clear()
+            o, c = self.o, self.cfg
+            g = o.ReferenceGenerator(self.main, self.lib[:n_lib], self.og, c["diff"], 0, c["rr"], c["ra"])
+            tm = {}
+            g.generate([np.full_like(self.state, -1)], tm)  # also the first-touch warm-up of its buffers
+            g.generate([np.full_like(self.state, -1)], tm)
+            g.fixed_seconds = tm["seconds"]
+            self._gens[n_lib] = g
+        return self._gens[n_lib]
+
+    def state_of(self, cells):
+        st = np.full_like(self.state, -1)
+        for y, x in cells:
+            st[y, x] = 0
         return st
 
-    def counts(st):  # nominal / visited pixel-diffs of a sample: the C port's statistics (untimed; same logic, tests/)
-        cells, bounds, flips, _ = oracle.extract_cells(mains, og, 0, st)
-        r = oracle.generate_step(cfg["diff"], cells, bounds, flips, lib_f, og.detail_cells[0].masks4(), st, cfg["rr"], cfg["ra"],
-                                 want_D=False, early_exit=True)
-        return r.nominal, r.visited, time.perf_counter()
+    def _prepared(self, n_lib):
+        o, c = self.o, self.cfg
+        if getattr(self, "_prep_n", None) != n_lib:
+            self._mains = [o.to_working_space(self.main, c["diff"])]
+            self._lib_f = o.preprocess_library(self.lib[:n_lib], self.og, c["diff"])
+            self._prep_n = n_lib
+        return self._mains, self._lib_f
 
-    use_ref = oracle.reference_generator_available()
-    ref_gen = None
-    if use_ref:
-        try:  # a library built on another machine may not load / run here: fall back to the port and say so (kind = "port")
-            ref_gen = oracle.ReferenceGenerator(main, sub_lib, og, cfg["diff"], 0, cfg["rr"], cfg["ra"])
-            ref_gen.generate([np.full_like(state, -1)])
-        except Exception as e:  # noqa: BLE001
-            print("cpu baseline: reference object code unusable here (%s), timing the C port instead" % e, file=sys.stderr)
-            use_ref, ref_gen = False, None
+    def nominal(self, st, n_lib):
+        """nominal pixel-diffs of a sample: active (flipped mask) pixels inside each cell's detail-space bound x library images --
+        the unit the engine counts (mosaic_timings.pixel_diffs) and the C port reports as `nominal`"""
+        o = self.o
+        _, bounds, flips, _ = o.extract_cells([np.zeros(self.main.shape, np.float32)], self.og, 0, st)
+        m4 = self.og.detail_cells[0].masks4()
+        act = 0
+        for (bx, by, bw, bh), f in zip(np.asarray(bounds).reshape(-1, 4), np.asarray(flips).ravel()):
+            act += int(np.count_nonzero(m4[f][by:by + bh, bx:bx + bw]))
+        return act * n_lib
 
-    def timed(st):
-        if use_ref:
-            tm = {}
-            ref_gen.generate([st], tm)  # setGridState + generateBestFits (preprocessing included, as in the reference) + getBestFits
-            return tm["seconds"]
-        cells, bounds, flips, _ = oracle.extract_cells(mains, og, 0, st)
-        masks4 = og.detail_cells[0].masks4()
+    def counts(self, st, n_lib):
+        """nominal / visited pixel-diffs of a sample from the C port's statistics (untimed; same loops, pinned in tests/)"""
+        o, c = self.o, self.cfg
+        mains, lib_f = self._prepared(n_lib)
+        cells, bounds, flips, _ = o.extract_cells(mains, self.og, 0, st)
+        r = o.generate_step(c["diff"], cells, bounds, flips, lib_f, self.og.detail_cells[0].masks4(), st, c["rr"], c["ra"],
+                            want_D=False, early_exit=True)
+        return r.nominal, r.visited
+
+    def timed(self, cells, n_lib):
+        """seconds of the best-fit loops for `cells` x the first n_lib images (fixed per-call preprocessing subtracted)"""
+        st = self.state_of(cells)
+        if self.use_ref:
+            try:
+                g = self._gen(n_lib)
+                tm = {}
+                g.generate([st], tm)
+                return max(tm["seconds"] - g.fixed_seconds, 1e-9), g.fixed_seconds, "reference"
+            except Exception as e:  # noqa: BLE001  -- a library built on another machine may not load / run here
+                print("cpu baseline: reference object code unusable here (%s), timing the C port instead" % e, file=sys.stderr)
+                self.use_ref = False
+        o, c = self.o, self.cfg
+        mains = [o.to_working_space(self.main, c["diff"])]
+        lib_f = o.preprocess_library(self.lib[:n_lib], self.og, c["diff"])
+        cl, bounds, flips, _ = o.extract_cells(mains, self.og, 0, st)
+        m4 = self.og.detail_cells[0].masks4()
         t1 = time.perf_counter()
-        oracle.generate_step(cfg["diff"], cells, bounds, flips, lib_f, masks4, st, cfg["rr"], cfg["ra"], want_D=False, early_exit=True)
-        return time.perf_counter() - t1
+        o.generate_step(c["diff"], cl, bounds, flips, lib_f, m4, st, c["rr"], c["ra"], want_D=False, early_exit=True)
+        return time.perf_counter() - t1, 0.0, "port"
 
-    # fixed cost of a call (the reference preprocesses the WHOLE main image and library inside generateBestFits; at full size that
-    # is amortised over 2,040 cells x 10,000 images, in this small sample it is not): measured with an empty grid state and
-    # subtracted, which only favours the CPU number
-    fixed = timed(first_rows(0)) if use_ref else 0.0
-    # calibrate on one grid row, then time as many rows as fit the budget in ONE call (repeat penalties across rows included)
-    one = max(timed(first_rows(1)) - fixed, 1e-9)
-    k = max(1, min(len(valid_rows), int(seconds / one)))
-    st = first_rows(k)
-    elapsed = one if k == 1 else max(timed(st) - fixed, 1e-9)
-    nominal, visited, _ = counts(st)
-    cells_done = int((st >= 0).sum())
-    if ref_gen is not None:
-        ref_gen.close()
-    return {"seconds": elapsed, "prep_seconds": prep_s, "visited": visited, "nominal": nominal, "rows": k, "n_lib": n_lib,
-            "kind": "reference" if use_ref else "port",
-            "sample": "first %d grid row(s) with valid cells (%d cells) x first %d library images of the workload, early exit on%s"
-                      % (k, cells_done, n_lib, "; fixed per-call preprocessing of the whole main image (%.2f s) subtracted" % fixed
-                         if use_ref else "")}
+    def sample(self, cells, n_lib, what, want_visited=True):
+        secs, fixed, kind = self.timed(cells, n_lib)
+        st = self.state_of(cells)
+        if want_visited:
+            nominal, visited = self.counts(st, n_lib)
+            assert nominal == self.nominal(st, n_lib)
+        else:
+            nominal, visited = self.nominal(st, n_lib), None
+        return {"seconds": secs, "nominal": nominal, "visited": visited, "kind": kind, "cells": len(cells), "n_lib": n_lib,
+                "nominal_per_s": nominal / secs, "visited_per_s": visited / secs if want_visited else None,
+                "visited_fraction": visited / max(nominal, 1) if want_visited else None,
+                "sample": "%s: %d cell(s) x %s%d library images of the workload, early exit on%s"
+                          % (what, len(cells), "all " if n_lib == len(self.lib) else "the first ", n_lib,
+                             "; fixed per-call preprocessing of the whole main image and library (%.2f s) subtracted" % fixed
+                             if kind == "reference" else "")}
+
+    def close(self):
+        for g in self._gens.values():
+            g.close()
+        self._gens.clear()
 
 
 CPU_NOTE = {
-    "reference": "the reference's own PhotomosaicGeneratorBase.cpp + CPUPhotomosaicGenerator.cpp + ColourDifference.cpp + "
-                 "GridUtility.cpp compiled unmodified (oracle/_ref/libref_core.so, recipe oracle/Makefile), OpenCV calls inside "
-                 "them answered by cv2; the timed call is generateBestFits() incl. its preprocessing; 1 thread because "
-                 "CPUPhotomosaicGenerator is single-threaded; value counts nominal pixel-diffs (early exit credited), "
-                 "visited_per_s the differences actually evaluated",
-    "port": "oracle/mosaic_oracle.c (plain-C restatement; the reference-compiled library oracle/_ref/libref_core.so is absent), "
-            "1 thread because CPUPhotomosaicGenerator is single-threaded; value counts nominal pixel-diffs (early exit "
-            "credited), visited_per_s the differences actually evaluated",
+    "reference": "the reference's own PhotomosaicGeneratorBase.cpp + CPUPhotomosaicGenerator.cpp + ColourDifference.cpp + GridUtility.cpp "
+                 "compiled unmodified (oracle/_ref/libref_core.so, recipe oracle/Makefile), OpenCV calls inside them answered by cv2; 1 "
+                 "thread because CPUPhotomosaicGenerator is single-threaded; value counts NOMINAL pixel-diffs (what the early exit skips "
+                 "is credited), visited_per_s the differences actually evaluated",
+    "port": "oracle/mosaic_oracle.c (plain-C restatement; the reference-compiled library oracle/_ref/libref_core.so is absent), 1 thread; "
+            "value counts nominal pixel-diffs (early exit credited), visited_per_s the differences actually evaluated",
 }
 
 
-def run_reference(args, cfg):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def cpu_baseline(cfg, main, lib, seconds):
+    """(A) the first cells of the grid x the FULL library and (B) one grid row x 256 images; A is the headline."""
+    ref = CpuReference(cfg, main, lib)
+    n_full = len(lib)
+    probe_n = min(n_full, 256)
+    t_probe, _, _ = ref.timed(ref.valid[:1], probe_n)                      # calibrate: one cell x 256 images
+    per_cell_full = t_probe * n_full / probe_n
+    k = int(max(1, min(len(ref.valid), seconds / max(per_cell_full, 1e-9))))
+    a = ref.sample(ref.valid[:k], n_full, "A")
+    row0 = [c for c in ref.valid if c[0] == ref.valid[0][0]]
+    b = ref.sample(row0, probe_n, "B (first grid row)")
+    ref.close()
+    return {"value": a["nominal_per_s"], "unit": "pixel-diffs/s", "cores": 1, "kind": a["kind"], "sample": a["sample"],
+            "visited_per_s": a["visited_per_s"], "visited_fraction": a["visited_fraction"], "seconds": a["seconds"],
+            "second_sample": {k2: b[k2] for k2 in ("sample", "nominal_per_s", "visited_per_s", "visited_fraction", "seconds")},
+            "note": CPU_NOTE[a["kind"]]}
+
+
+def run_reference(args, name, cfg):
+    """--impl reference: every step times the reference's CPU generator on a bounded sample of the workload -- a different cell of
+    the first grid row each step x as much of the library as the per-step budget allows (the FULL library when it fits), so that
+    the whole --steps/--warmup run ends within a few minutes."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    from mosaicmagnifique_b200 import synthetic
-    main = synthetic.make_main_image(cfg["h"], cfg["w"], cfg["seed"] + 1000)
-    lib = synthetic.make_library(min(cfg["n_lib"], 256), cfg["cell"], cfg["seed"])
-    per_step = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        cpu_sample(cfg, main, lib, 0.0)
+    main, lib = make_inputs(cfg)
+    ref = CpuReference(cfg, main, lib)
+    n_full = len(lib)
+    budget = max(3.0, 240.0 / max(1, args.steps + args.warmup))             # seconds per step
+    probe_n = min(n_full, 256)
+    t_probe, _, _ = ref.timed(ref.valid[:1], probe_n)
+    per_cell_full = t_probe * n_full / probe_n
+    if per_cell_full <= budget:
+        n_lib, k = n_full, int(max(1, min(8, budget / per_cell_full)))
+    else:
+        n_lib, k = int(max(probe_n, min(n_full, n_full * budget / per_cell_full))), 1
+    cells_of = lambda i: [ref.valid[(i * k + j) % len(ref.valid)] for j in range(k)]
+    for i in range(args.warmup):
+        ref.timed(cells_of(i), n_lib)
     t0 = time.perf_counter()
-    tot_nominal = tot_visited = 0
+    tot_nominal = 0
     tot_s = 0.0
     last = None
-    for _ in range(args.steps):
-        last = cpu_sample(cfg, main, lib, per_step)
+    for i in range(args.steps):
+        # the evaluated ("visited") share is measured on the last step's sample only: it needs a second, untimed run of the loops
+        last = ref.sample(cells_of(args.warmup + i), n_lib, "per step", want_visited=(i == args.steps - 1))
         tot_nominal += last["nominal"]
-        tot_visited += last["visited"]
         tot_s += last["seconds"]
     wall = time.perf_counter() - t0
+    ref.close()
     value = tot_nominal / tot_s
     out = {"impl": "reference", "metric": "pixel-diffs/sec", "value": value, "unit": "pixel-diffs/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": cfg["desc"], "sample": last["sample"]},
+           "config": describe(cfg, name, args.gpus),
            "cpu_baseline": {"value": value, "unit": "pixel-diffs/s", "cores": 1, "kind": last["kind"], "sample": last["sample"],
-                            "visited_per_s": tot_visited / tot_s, "note": CPU_NOTE[last["kind"]]},
+                            "visited_per_s": value * last["visited_fraction"], "visited_fraction": last["visited_fraction"],
+                            "note": CPU_NOTE[last["kind"]]},
            "e2e": {"value": value, "unit": "pixel-diffs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0, "wall_s": wall}
     print(json.dumps(out))
@@ -259,18 +373,216 @@ def run_reference(args, cfg):
 
 # ----------------------------------------------------------------------------- the B200 arm
 
+def sass_counts():
+    """Executed work per pixel-difference of the two difference kernels, counted from the SASS of the library by
+    tools/sass_counts.py (committed artefact profiles/r2_sass_counts.json + the loop listings next to it)."""
+    path = os.path.join(ROOT, "profiles", "r2_sass_counts.json")
+    d = json.load(open(path))
+    from mosaicmagnifique_b200 import library_path
+    sha = hashlib.sha256(open(library_path(), "rb").read()).hexdigest()
+    return d, os.path.relpath(path, ROOT), sha == d.get("library_sha256")
+
+
+class B200Run:
+    """One workload on this rank's GPU through the reference-shaped API."""
+
+    def __init__(self, name, cfg, rank, world, local_rank):
+        import torch
+        from mosaicmagnifique_b200 import CellGroup, PhotomosaicGenerator
+        self.torch = torch
+        self.name, self.cfg, self.rank, self.world, self.local_rank = name, cfg, rank, world, local_rank
+        H, W, N, S = cfg["h"], cfg["w"], cfg["n_lib"], cfg["cell"]
+        # synthetic inputs, identical on every rank (seeded), in PINNED host memory for the e2e leg
+        self.main_t = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+        self.lib_t = torch.empty((N, S, S, 3), dtype=torch.uint8).pin_memory()
+        make_inputs(cfg, self.main_t.numpy(), self.lib_t.numpy())
+        self.gen = gen = PhotomosaicGenerator(local_rank)
+        cg = CellGroup()
+        cg.setCellShape(make_shape(cfg))
+        cg.setDetail(cfg["detail"])
+        cg.setSizeSteps(cfg.get("steps", 0))
+        gen.setColourDifference(cfg["diff"])
+        gen.setCellGroup(cg)
+        gen.setRepeat(cfg["rr"], cfg["ra"])
+        self.h2d_lib = self.lib_t.numel()
+        self.h2d_main = self.main_t.numel()
+        self.load_inputs(first=True)
+        self.state = gen.computeGridState()
+        self.valid_cells = int(sum((s >= 0).sum() for s in self.state))
+
+    def load_inputs(self, first=False):
+        from mosaicmagnifique_b200.parallel import set_library_sharded, set_main_image_sharded
+        gen, cfg = self.gen, self.cfg
+        H, W, N, S = cfg["h"], cfg["w"], cfg["n_lib"], cfg["cell"]
+        if self.world > 1:
+            # every rank uploads only what it computes on: 1/world of the library over PCIe (reduced to the detail size on the GPU,
+            # the rest arrives over NVLink, one in-place NCCL all-gather) and the main-image rows its cells read. The grid state is
+            # an input of generateBestFits (setGridState), so the rows are known before the upload; the very first load brings the
+            # whole image because computeGridState's entropy rule reads all of it.
+            self.h2d_lib = set_library_sharded(gen, self.lib_t, self.rank, self.world)
+            if first:
+                gen.setMainImagePtr(self.main_t.data_ptr(), H, W, W * 3)
+            else:
+                gen.setGridState(self.state)
+                gen.setShard(self.rank, self.world)
+                self.h2d_main = set_main_image_sharded(gen, self.main_t)
+        else:
+            gen.setMainImagePtr(self.main_t.data_ptr(), H, W, W * 3)
+            gen.setLibraryPtr(self.lib_t.data_ptr(), N, S)
+
+    def step(self):
+        from mosaicmagnifique_b200.parallel import generate_sharded
+        gen = self.gen
+        gen.setGridState(self.state)
+        if self.world > 1:
+            grids, _ = generate_sharded(gen, self.rank, self.world)
+        else:
+            assert gen.generateBestFits()
+            grids = gen.getBestFits()
+        return grids
+
+    def barrier(self):
+        torch = self.torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(self, vals):
+        if self.world == 1:
+            return list(vals)
+        t = self.torch.tensor(list(vals), device="cuda", dtype=self.torch.float64)
+        self.torch.distributed.all_reduce(t, op=self.torch.distributed.ReduceOp.MAX)
+        return t.tolist()
+
+    def measure(self, steps, warmup, e2e_steps, sample_clocks):
+        gen = self.gen
+        for _ in range(warmup):
+            grids = self.step()
+        clocks = ClockSampler(self.local_rank) if sample_clocks else None
+        self.barrier()
+        if clocks:
+            clocks.start()
+        t0 = time.perf_counter()
+        phase = {"preprocess_ms": 0.0, "diff_ms": 0.0, "select_ms": 0.0}
+        launches = 0
+        for _ in range(steps):
+            grids = self.step()
+            tm = gen.getTimings()
+            for k in phase:
+                phase[k] += tm[k]
+            launches += tm["kernel_launches"]
+        self.barrier()
+        elapsed = time.perf_counter() - t0
+        clk = clocks.stop() if clocks else None
+        pixel_diffs = tm["pixel_diffs"]  # whole job (every rank counts all cells of the step)
+        local_share = 1.0
+        if self.world > 1:
+            info = gen.candidateInfo(0)
+            local_share = info["n_cells"] / max(1, info["n_valid"])
+        elapsed, phase["diff_ms"], phase["preprocess_ms"], phase["select_ms"] = self.allmax(
+            [elapsed, phase["diff_ms"], phase["preprocess_ms"], phase["select_ms"]])
+
+        # ---- end-to-end leg: pinned host buffers in, grid out, every step
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            self.load_inputs()
+            grids = self.step()
+            checksum = int(sum(int(g.sum()) for g in grids))  # touch the D2H result
+        self.barrier()
+        (e2e_elapsed,) = self.allmax([time.perf_counter() - t0])
+        return {"elapsed": elapsed, "steps": steps, "phase": phase, "launches": int(launches), "pixel_diffs": pixel_diffs,
+                "pixel_diffs_nominal": tm["pixel_diffs_nominal"], "local_share": local_share, "clocks": clk, "e2e_elapsed": e2e_elapsed,
+                "e2e_steps": e2e_steps, "checksum": checksum, "h2d": int(self.h2d_main + self.h2d_lib),
+                "d2h": int(sum(g.size * 8 for g in grids))}
+
+    def tie_band(self):
+        """cells whose best two penalised candidates are within an FP32-explainable tolerance (untimed, 1 GPU)"""
+        gen = self.gen
+        gen.setReportMargins(True)
+        gen.setGridState(self.state)
+        assert gen.generateBestFits()
+        rel = []
+        for stp in range(len(self.state)):
+            b, s2 = gen.getMargins(stp)
+            rel.append((s2.astype(np.float64) - b) / np.maximum(b.astype(np.float64), 1e-30))
+        gen.setReportMargins(False)
+        rel = np.concatenate(rel) if rel else np.zeros(0)
+        return {"of": int(rel.size), "cells_within": {"1e-4": int((rel <= 1e-4).sum()), "1e-5": int((rel <= 1e-5).sum()),
+                                                      "1e-6": int((rel <= 1e-6).sum())},
+                "tolerance_relative": 1e-5, "cells": int((rel <= 1e-5).sum()),
+                "note": "cells whose best and second-best penalised scores differ by <= tol relative: only there may the FP32 engine and "
+                        "the f64 reference legitimately pick different images (tests/helpers/parity.py uses 1e-5)"}
+
+    def close(self):
+        self.gen.close()
+        del self.main_t, self.lib_t
+
+
+def roofline_of(name, cfg, m, mb, peaks, sass, world):
+    """Roofline of the workload's difference kernel from live numbers: executed pipe work (SASS counts) / CUDA-event duration."""
+    kern = "diff_sum" if cfg["diff"] == 2 else "diff_euclid"
+    per = sass[0]["kernels"][kern]["per_pixel_diff"]
+    diff_s = m["phase"]["diff_ms"] * 1e-3 / m["steps"]          # all diff launches of one step on the slowest rank (CUDA events)
+    units = m["pixel_diffs"] * m["local_share"]                  # pixel-diffs those launches process on one GPU
+    fp32_rate, mufu_rate = per["fp32_lane_ops"] * units / diff_s, per["mufu"] * units / diff_s
+    f_fp32, f_mufu = fp32_rate / mb[1], mufu_rate / mb[2]
+    work = WORK_REFERENCE_FORMULA[cfg["diff"]]
+    N = cfg["n_lib"]
+    out = {"kernel": kern + "_kernel", "kernel_ms": diff_s * 1e3, "launches_per_step": 1 + cfg.get("steps", 0),
+           "bound": "fp32-pipe" if f_fp32 >= f_mufu else "mufu-pipe",
+           "achieved": (fp32_rate if f_fp32 >= f_mufu else mufu_rate) / 1e12,
+           "peak": (mb[1] if f_fp32 >= f_mufu else mb[2]) / 1e12,
+           "unit": "T lane-op/s" if f_fp32 >= f_mufu else "T MUFU-op/s",
+           "frac": max(f_fp32, f_mufu),
+           "executed_fp32": {"lane_ops_per_pixel_diff": per["fp32_lane_ops"], "achieved_per_s": fp32_rate, "peak_per_s": mb[1], "frac": f_fp32},
+           "executed_mufu": {"ops_per_pixel_diff": per["mufu"], "achieved_per_s": mufu_rate, "peak_per_s": mb[2], "frac": f_mufu},
+           "counts_source": "%s (cuobjdump -sass of the shipped library, tools/sass_counts.py; matches the loaded library: %s)" % (sass[1], sass[2]),
+           "peak_source": "live in-library micro-benchmark (FFMA2 lane-ops/s, MUFU.RSQ ops/s) on this GPU at its current clocks",
+           "pixel_diffs_per_s_kernel": units / diff_s,
+           "frac_reference_formula": work["sfu"] * units / diff_s / mb[2],
+           "reference_formula_note": "SURVEY 8d counts the REFERENCE formula (%d flop + %d special-function ops per pixel-diff); the kernel's "
+                                     "algebra executes fewer, so this ratio is not a pipe utilisation and may exceed 1" % (work["flop"], work["sfu"]),
+           "traffic": NCU_TRAFFIC[name][0] if (world == 1 and name in NCU_TRAFFIC) else None,
+           "traffic_source": NCU_TRAFFIC[name][1] if (world == 1 and name in NCU_TRAFFIC) else None}
+    if cfg["diff"] == 2:
+        out["mixed_pipe_ceiling_pixel_diffs_per_s"] = mb[6]
+    # secondary bound: bytes the launch must move at least once (packed library + packed cells of the top level)
+    ds = int(cfg["cell"] * cfg["detail"] / 100)
+    lib_b, cell_b = (16, 20) if cfg["diff"] == 2 else (12, 16)
+    act = m["pixel_diffs"] / max(m["pixel_diffs_nominal"], 1)    # active share of the detail cell (mask + bounds)
+    min_bytes = (N * lib_b + m["valid_cells"] * m["local_share"] * cell_b) * ds * ds * min(1.0, act * 1.02)
+    out["hbm"] = {"min_bytes_per_step": min_bytes, "achieved_gbs": min_bytes / diff_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                  "frac": (min_bytes / diff_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                  "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"}
+    return out
+
+
+def summarise(name, cfg, m, world, roof):
+    sec = m["elapsed"] / m["steps"]
+    return {"config": describe(cfg, name, world), "value": m["pixel_diffs"] / sec, "unit": "pixel-diffs/s", "generate_ms": 1e3 * sec,
+            "steps": m["steps"], "valid_cells": m["valid_cells"], "pixel_diffs_per_step": m["pixel_diffs"],
+            "phases_ms_per_step": {k: v / m["steps"] for k, v in m["phase"].items()},
+            "e2e": {"value": m["pixel_diffs"] / (m["e2e_elapsed"] / m["e2e_steps"]), "unit": "pixel-diffs/s",
+                    "ms_per_step": 1e3 * m["e2e_elapsed"] / m["e2e_steps"], "steps": m["e2e_steps"], "h2d_bytes_per_step": m["h2d"],
+                    "d2h_bytes_per_step": m["d2h"], "result_checksum": m["checksum"]},
+            "gpu_launches": m["launches"], "roofline": roof}
+
+
 def main():
     args = parse()
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, cfg)
+        run_reference(args, args.workload, cfg)
         return
+
+    import ctypes
 
     import torch
     import torch.distributed as dist
 
-    from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator, capi, synthetic
-    from mosaicmagnifique_b200.parallel import generate_sharded, set_library_sharded
+    from mosaicmagnifique_b200 import capi
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,183 +593,58 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # synthetic inputs, identical on every rank (seeded), in PINNED host memory for the e2e leg
-    H, W, N, S = cfg["h"], cfg["w"], cfg["n_lib"], cfg["cell"]
-    main_t = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
-    lib_t = torch.empty((N, S, S, 3), dtype=torch.uint8).pin_memory()
-    main_np, lib_np = main_t.numpy(), lib_t.numpy()
-    main_np[...] = synthetic.make_main_image(H, W, cfg["seed"] + 1000)
-    synthetic.make_library(N, S, cfg["seed"], out=lib_np)
-
-    gen = PhotomosaicGenerator(local_rank)
-    cg = CellGroup()
-    cg.setCellShape(make_shapes(cfg)[0])
-    cg.setDetail(cfg["detail"])
-    cg.setSizeSteps(cfg.get("steps", 0))
-    gen.setColourDifference(cfg["diff"])
-    gen.setCellGroup(cg)
-    gen.setRepeat(cfg["rr"], cfg["ra"])
-
-    h2d_lib = [lib_t.numel()]
-
-    def load_inputs():
-        gen.setMainImagePtr(main_t.data_ptr(), H, W, W * 3)
-        if world > 1:
-            # replicated library: each rank uploads 1/world over PCIe, the rest arrives over NVLink (NCCL all-gather)
-            h2d_lib[0] = set_library_sharded(gen, lib_t, rank, world)
-        else:
-            gen.setLibraryPtr(lib_t.data_ptr(), N, S)
-
-    load_inputs()
-    state = gen.computeGridState()
-    valid_cells = int(sum((s >= 0).sum() for s in state))
-
-    def step():
-        gen.setGridState(state)
-        if world > 1:
-            grids, _ = generate_sharded(gen, rank, world)
-        else:
-            assert gen.generateBestFits()
-            grids = gen.getBestFits()
-        return grids
-
-    # ---- device-resident leg
-    for _ in range(args.warmup):
-        grids = step()
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    t0 = time.perf_counter()
-    phase = {"preprocess_ms": 0.0, "diff_ms": 0.0, "select_ms": 0.0}
-    launches = 0
-    for _ in range(args.steps):
-        grids = step()
-        tm = gen.getTimings()
-        for k in phase:
-            phase[k] += tm[k]
-        launches += tm["kernel_launches"]
-    barrier()
-    elapsed = time.perf_counter() - t0
-    clk = clocks.stop()
-    pixel_diffs = tm["pixel_diffs"]          # whole job (every rank counts all cells of the step)
-    local_share = 1.0
-    if world > 1:
-        t = torch.tensor([elapsed, phase["diff_ms"], phase["preprocess_ms"], phase["select_ms"]], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed, phase["diff_ms"], phase["preprocess_ms"], phase["select_ms"] = t.tolist()
-        info = gen.candidateInfo(0)
-        local_share = info["n_cells"] / max(1, info["n_valid"])
-    ms_per_step = 1e3 * elapsed / args.steps
-    value = pixel_diffs / (elapsed / args.steps)
-
-    # ---- end-to-end leg: pinned host buffers in, grid out, every step
-    e2e_steps = max(1, min(args.steps, 3))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        load_inputs()
-        grids = step()
-        checksum = int(sum(int(g.sum()) for g in grids))  # touch the D2H result
-    barrier()
-    e2e_elapsed = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_elapsed = t.item()
-    e2e_value = pixel_diffs / (e2e_elapsed / e2e_steps)
-    h2d = int(main_t.numel() + h2d_lib[0])  # per rank
-    d2h = int(sum(g.size * 8 for g in grids))
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel (diff_sum), live numbers
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    sass = sass_counts()
+
+    # ---- headline workload
+    run = B200Run(args.workload, cfg, rank, world, local_rank)
+    m = run.measure(args.steps, args.warmup, max(1, min(args.steps, 3)), sample_clocks=True)
+    m["valid_cells"] = run.valid_cells
     mb = np.zeros(12)
-    import ctypes
     capi().mosaic_kernel_microbench(local_rank, mb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 12)
-    diff_s = phase["diff_ms"] * 1e-3 / args.steps                  # average duration of the one diff launch per step (CUDA events)
-    units_per_launch = pixel_diffs * local_share                    # pixel-diffs the launch on this GPU processes
-    work = WORK[cfg["diff"]]
-    sfu_rate = work["sfu"] * units_per_launch / diff_s              # reference-formula special-function ops / s
-    flop_rate = work["flop"] * units_per_launch / diff_s
-    ds = int(S * cfg["detail"] / 100)
-    min_bytes = (N * ds * ds * 16 + valid_cells * local_share * ds * ds * 20)  # library + cells read once (packed layout, top level)
-    roofline = {
-        "bound": "mufu", "kernel": "diff_sum_kernel",
-        "achieved": sfu_rate / 1e9, "peak": mb[2] / 1e9, "unit": "Gop/s", "frac": sfu_rate / mb[2],
-        "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None,
-        "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum; profiles/r1_diff_sum_ciede2000_v4_cfg4.txt, r1_dram_traffic_cfg5_final.csv)",
-        "note": "SURVEY 8d counts the REFERENCE formula: %d flop + %d special-function ops per pixel-diff; peak = MUFU.RSQ rate "
-                "measured live by the in-library micro-benchmark (16 lanes/clk/SM). The kernel's trig-free CIEDE2000 executes only "
-                "%d MUFU ops and %d FP32 lane-ops per pixel-diff, which is why frac can exceed 1; see executed_* (pipe utilisation "
-                "of what actually runs) and mixed_pipe_ceiling (a synthetic loop with the kernel's instruction mix)"
-                % (work["flop"], work["sfu"], EXECUTED[cfg["diff"]]["mufu"], EXECUTED[cfg["diff"]]["fp32_lane_ops"]),
-        "fp32": {"achieved_tflops": flop_rate / 1e12, "peak_tflops": 2 * mb[1] / 1e12, "frac": flop_rate / (2 * mb[1]),
-                 "peak_source": "live FFMA2 micro-benchmark x 2 flop"},
-        "executed_mufu": {"achieved_gops": EXECUTED[cfg["diff"]]["mufu"] * units_per_launch / diff_s / 1e9, "peak_gops": mb[2] / 1e9,
-                          "frac": EXECUTED[cfg["diff"]]["mufu"] * units_per_launch / diff_s / mb[2]},
-        "executed_fp32": {"achieved_lane_ops_per_s": EXECUTED[cfg["diff"]]["fp32_lane_ops"] * units_per_launch / diff_s,
-                          "peak_lane_ops_per_s": mb[1], "frac": EXECUTED[cfg["diff"]]["fp32_lane_ops"] * units_per_launch / diff_s / mb[1],
-                          "peak_source": "live FFMA2 micro-benchmark (packed FP32 lane-ops/s)"},
-        "mixed_pipe_ceiling_pixel_diffs_per_s": mb[6] if cfg["diff"] == 2 else None,
-        "hbm": {"min_bytes_per_launch": min_bytes, "achieved_gbs": min_bytes / diff_s / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                "frac": (min_bytes / diff_s / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                "peak_source": "MEASURED_PEAKS.json" if peaks else "absent"},
-        "pixel_diffs_per_s_kernel": units_per_launch / diff_s,
-        "reference_formula_ceiling_pixel_diffs_per_s": mb[2] / work["sfu"],
-        "kernel_ms": diff_s * 1e3,
-    }
+    head = summarise(args.workload, cfg, m, world, roofline_of(args.workload, cfg, m, mb, peaks, sass, world))
+    tie = run.tie_band() if world == 1 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(cfg, run.main_t.numpy(), run.lib_t.numpy(), args.cpu_seconds)
+    run.close()
+    del run
+    torch.cuda.empty_cache()
 
-    out = {"metric": "pixel-diffs/sec", "value": value, "unit": "pixel-diffs/s", "n_gpus": world, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": cfg["desc"], "name": args.workload, "valid_cells": valid_cells, "library": N, "cell": S,
-                      "detail": cfg["detail"], "colour_difference": ["RGB_EUCLIDEAN", "CIE76", "CIEDE2000"][cfg["diff"]],
-                      "repeat": [cfg["rr"], cfg["ra"]], "pixel_diffs_per_step": pixel_diffs,
-                      "cache": "inputs (%.1f GB packed library + cells per step) exceed the 126 MB L2; nothing is reused across steps"
-                               % (min_bytes / 1e9),
-                      "parallelism": "valid cells (raster order) sharded over %d GPU(s), library replicated (e2e: uploaded in 1/N slices "
-                                     "and all-gathered over NVLink), top-K candidates all-gathered (NCCL)" % world
-                      if world > 1 else "1 GPU"},
-           "generate_ms": ms_per_step,
-           "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
-           "e2e": {"value": e2e_value, "unit": "pixel-diffs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "ms_per_step": 1e3 * e2e_elapsed / e2e_steps, "steps": e2e_steps, "result_checksum": checksum},
-           "gpu_launches": int(launches),
-           "clocks": clk, "roofline": roofline,
-           "microbench": {"ffma_lane_ops_per_s": mb[0], "ffma2_lane_ops_per_s": mb[1], "mufu_rsq_per_s": mb[2], "mufu_ex2_per_s": mb[3],
-                          "sm_count": int(mb[4]), "ciede_mix_pairs_per_s": mb[6]}}
+    # ---- the other BASELINE configurations, a few steps each
+    configs = {}
+    if args.configs == "all" and args.workload == "cfg4":
+        for name in SECONDARY:
+            c2 = WORKLOADS[name]
+            r2 = B200Run(name, c2, rank, world, local_rank)
+            m2 = r2.measure(min(args.steps, 5), 3, 2, sample_clocks=True)
+            m2["valid_cells"] = r2.valid_cells
+            s2 = summarise(name, c2, m2, world, roofline_of(name, c2, m2, mb, peaks, sass, world))
+            s2["clocks"] = m2["clocks"]
+            if world == 1:
+                s2["tie_band"] = r2.tie_band()
+            configs[name] = s2
+            r2.close()
+            del r2
+            torch.cuda.empty_cache()
 
-    if world == 1:
-        # tie band at full size (untimed): cells whose best two penalised candidates are within the FP32 tolerance
-        gen.setReportMargins(True)
-        gen.setGridState(state)
-        assert gen.generateBestFits()
-        n_tie = n_all = 0
-        for stp in range(len(state)):
-            b, s2 = gen.getMargins(stp)
-            n_all += len(b)
-            n_tie += int((((s2.astype(np.float64) - b) / np.maximum(b.astype(np.float64), 1e-30)) <= 1e-4).sum())
-        gen.setReportMargins(False)
-        out["tie_band"] = {"tolerance_relative": 1e-4, "cells": n_tie, "of": n_all,
-                           "note": "cells whose best and second-best penalised scores differ by <= 1e-4 relative: only there may "
-                                   "the FP32 engine and the f64 reference legitimately pick different images"}
-
-    if not args.no_cpu_baseline and world == 1:
-        cs = cpu_sample(cfg, main_np, lib_np, args.cpu_seconds)
-        out["cpu_baseline"] = {"value": cs["nominal"] / cs["seconds"], "unit": "pixel-diffs/s", "cores": 1, "kind": cs["kind"],
-                               "sample": cs["sample"], "visited_per_s": cs["visited"] / cs["seconds"], "seconds": cs["seconds"]}
-    print(json.dumps(out))
+    if rank == 0:
+        out = {"metric": "pixel-diffs/sec", "value": head["value"], "unit": "pixel-diffs/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": head["generate_ms"], "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": head["config"], "generate_ms": head["generate_ms"],
+               "valid_cells": head["valid_cells"], "pixel_diffs_per_step": head["pixel_diffs_per_step"],
+               "phases_ms_per_step": head["phases_ms_per_step"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+               "clocks": m["clocks"], "roofline": head["roofline"],
+               "microbench": {"ffma_lane_ops_per_s": mb[0], "ffma2_lane_ops_per_s": mb[1], "mufu_rsq_per_s": mb[2], "mufu_ex2_per_s": mb[3],
+                              "sm_count": int(mb[4]), "ciede_mix_pairs_per_s": mb[6]}}
+        if tie is not None:
+            out["tie_band"] = tie
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        if configs:
+            out["configs"] = configs
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 

@@ -115,7 +115,11 @@ int mosaic_build_photomosaic(mosaic_generator *g, const uint8_t background_bgra[
                              size_t row_stride);
 int mosaic_get_max_progress(const mosaic_generator *g);
 void mosaic_set_progress_callback(mosaic_generator *g, mosaic_progress_fn fn, void *user);
+/* cancel() (PhotomosaicGeneratorBase.cpp:217-220): callable from any thread and from inside the progress callback. The running
+ * difference kernel stops scheduling work (every CTA checks the flag when it starts), generate returns MOSAIC_ERR_CANCELLED within
+ * milliseconds. Like m_wasCanceled the flag is sticky: later generate calls return MOSAIC_ERR_CANCELLED until mosaic_reset_cancel. */
 void mosaic_cancel(mosaic_generator *g);
+void mosaic_reset_cancel(mosaic_generator *g);
 
 /* ---- parity / measurement taps (no reference counterpart; used by tests and bench.py) */
 /* keep the full difference matrix of every step on the device so it can be read back */
@@ -142,6 +146,25 @@ int mosaic_get_candidate_count(const mosaic_generator *g, int step, int64_t *fir
 int mosaic_get_candidates_device(const mosaic_generator *g, int step, void **scores, void **indices);
 /* selection over candidates of ALL cells of a step (device pointers, [n_valid][k]) -> best fits */
 int mosaic_select_from_candidates(mosaic_generator *g, int step, const void *scores, const void *indices, int k);
+/* The same exchange as ONE collective: every rank's candidates of a step are one device block of identical size
+ * {float scores [rows_per_rank][k], int32 indices [rows_per_rank][k]} (rank r owns the valid cells r * rows_per_rank ... of the
+ * step's raster order, a split every rank computes by itself); the blocks are all-gathered in rank order into one buffer
+ * (world * block_bytes) and handed to mosaic_select_from_gathered. No sizes are exchanged and nothing is read back. */
+int mosaic_get_candidate_block(const mosaic_generator *g, int step, void **block, int64_t *rows_per_rank, int *k, size_t *block_bytes);
+int mosaic_select_from_gathered(mosaic_generator *g, int step, const void *gathered_blocks, int k, int64_t rows_per_rank);
+/* Sharded inputs (end-to-end path of a multi-GPU run): a rank uploads only what it computes on.
+ * mosaic_get_shard_rows: main-image rows [row_lo, row_hi) that this handle's cells read (cell group, grid state and shard must
+ *   be set; rows x cols declares the image size). mosaic_set_main_image_rows: setMainImage from a pointer to row 0 of the FULL
+ *   image, copying only rows [row_lo, row_hi); generate fails with MOSAIC_ERR_NOT_READY if a needed row is missing.
+ * mosaic_set_library_shard: this rank's slice [first, first + count) of an n_total-image library at the cell size; it is stored
+ *   at the detail size of step 0 when detail != 100 % (resized on the GPU, PhotomosaicGeneratorBase.cpp:262-270) so that the
+ *   remaining slices, delivered by the caller into the buffer of mosaic_get_library_device (NCCL all-gather over NVLink, images
+ *   back to back at *stored_size, room for capacity_images >= n_total), cross the wire at the small size. */
+int mosaic_get_shard_rows(mosaic_generator *g, int rows, int cols, int *row_lo, int *row_hi);
+int mosaic_set_main_image_rows(mosaic_generator *g, const uint8_t *bgr, int rows, int cols, size_t row_stride, int row_lo, int row_hi);
+int mosaic_set_library_shard(mosaic_generator *g, const uint8_t *bgr_slice, int64_t first, int64_t count, int64_t n_total, int size,
+                             int64_t capacity_images);
+int mosaic_get_library_device(const mosaic_generator *g, void **ptr, int *stored_size, int64_t *capacity_images);
 
 /* ---- kernel-level entry points, mirroring the wrapper functions the reference's kernel tests call
  * (src/Photomosaic/CUDA/PhotomosaicGenerator.cuh:6-43, Reduction.cuh:23; test/tst_ColourDifference.h:233-543,

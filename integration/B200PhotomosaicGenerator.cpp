@@ -27,6 +27,8 @@ bool B200PhotomosaicGenerator::generateBestFits()
 {
     if (!m_engine || m_lib.empty() || m_bestFits.empty())
         return false;
+    if (m_wasCanceled)  // cancel() before the call: the reference's loops leave at their first check (CPUPhotomosaicGenerator.cpp:52)
+        return false;
     bool ok = true;
     auto chk = [&](int rc) { ok = ok && rc == MOSAIC_OK; };
 
@@ -63,10 +65,23 @@ bool B200PhotomosaicGenerator::generateBestFits()
         chk(mosaic_set_grid_state(m_engine, int(step), rows, cols, valid.data()));
     }
     chk(mosaic_set_repeat(m_engine, m_repeatRange, m_repeatAddition));
+    // progress(int) is emitted from inside mosaic_generate on this thread. A connected QProgressDialog runs the cancel() slot
+    // during the emission (it only sets m_wasCanceled, PhotomosaicGeneratorBase.cpp:217-220), so the flag is looked at right after
+    // and handed to the engine, whose running kernel then stops scheduling work.
     mosaic_set_progress_callback(
-        m_engine, [](int p, void *self) { emit static_cast<B200PhotomosaicGenerator *>(self)->progress(p); }, this);
+        m_engine,
+        [](int p, void *self) {
+            B200PhotomosaicGenerator *gen = static_cast<B200PhotomosaicGenerator *>(self);
+            emit gen->progress(p);
+            if (gen->m_wasCanceled)
+                mosaic_cancel(gen->m_engine);
+        },
+        this);
 
-    if (!ok || mosaic_generate(m_engine) != MOSAIC_OK)
+    const int rc = ok ? mosaic_generate(m_engine) : MOSAIC_ERR_INVALID_ARGUMENT;
+    if (rc == MOSAIC_ERR_CANCELLED || m_wasCanceled)
+        return false;  // as both reference back-ends: `return !m_wasCanceled` (CPUPhotomosaicGenerator.cpp:107-112)
+    if (rc != MOSAIC_OK)
     {
         LogCritical(mosaic_last_error(m_engine));  // errors: text instead of the modal box of CUDAUtility.h:34-62
         return false;
@@ -84,5 +99,5 @@ bool B200PhotomosaicGenerator::generateBestFits()
                                              ? std::nullopt
                                              : std::optional<size_t>(size_t(out[size_t(y) * cols + x]));
     }
-    return true;
+    return !m_wasCanceled;
 }

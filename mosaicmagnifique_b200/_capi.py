@@ -70,6 +70,7 @@ def capi():
         "mosaic_get_max_progress": (i, [vp]),
         "mosaic_set_progress_callback": (None, [vp, PROGRESS_FN, vp]),
         "mosaic_cancel": (None, [vp]),
+        "mosaic_reset_cancel": (None, [vp]),
         "mosaic_set_keep_differences": (i, [vp, i]),
         "mosaic_get_valid_cell_count": (i64, [vp, i]),
         "mosaic_get_differences": (i, [vp, i, vp, i64, i64]),
@@ -81,6 +82,12 @@ def capi():
         "mosaic_get_candidate_count": (i, [vp, i, i64p, i64p, ip]),
         "mosaic_get_candidates_device": (i, [vp, i, c.POINTER(vp), c.POINTER(vp)]),
         "mosaic_select_from_candidates": (i, [vp, i, vp, vp, i]),
+        "mosaic_get_candidate_block": (i, [vp, i, c.POINTER(vp), i64p, ip, c.POINTER(sz)]),
+        "mosaic_select_from_gathered": (i, [vp, i, vp, i, i64]),
+        "mosaic_get_shard_rows": (i, [vp, i, i, ip, ip]),
+        "mosaic_set_main_image_rows": (i, [vp, vp, i, i, sz, i, i]),
+        "mosaic_set_library_shard": (i, [vp, vp, i64, i64, i64, i, i64]),
+        "mosaic_get_library_device": (i, [vp, c.POINTER(vp), ip, i64p]),
         "mosaic_kernel_colour_difference": (i, [i, i, vp, vp, i64, vp]),
         "mosaic_kernel_image_difference_sum": (i, [i, i, vp, vp, i64, vp, i, vp, vp]),
         "mosaic_kernel_select": (i, [i, vp, i64, vp, i, i, i, i]),

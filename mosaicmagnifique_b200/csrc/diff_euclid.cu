@@ -75,11 +75,12 @@ __device__ __forceinline__ float comp(const float4 &v, int i) { return i == 0 ? 
 __global__ void __launch_bounds__(kEThreads, 2)
 diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char *__restrict__ lib, float *__restrict__ D,
                    unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells,
-                   int n_cell_tiles, int n_lib_tiles)
+                   int n_cell_tiles, int n_lib_tiles, const int *__restrict__ cancel, unsigned long long *__restrict__ progress)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_bar[kEStages];
     __shared__ uint64_t empty_bar[kEStages];
+    __shared__ int s_cancelled;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int cell_tile, lib_tile;
@@ -91,8 +92,11 @@ diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char 
             mbar_init_e(&empty_bar[s], kEConsumerWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_cancelled = cancel ? load_cancel_flag(cancel) : 0;
     }
     __syncthreads();
+    if (s_cancelled)
+        return;  // cancel(): nothing has been issued yet, the whole CTA leaves
 
     if (warp == kEConsumerWarps) {
         if (lane == 0) {
@@ -170,10 +174,13 @@ diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char 
                 atomicMin(best_key + cell, key);
         }
     }
+    if (progress && threadIdx.x == 0)
+        atomicAdd(progress, 1ull);
 }
 
 cudaError_t launch_diff_euclid(const void *cells, const void *lib, float *D, unsigned long long *best_key, int n_cell_tiles,
-                               int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream)
+                               int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream, const int *cancel,
+                               unsigned long long *progress)
 {
     if (n_cell_tiles <= 0 || n_lib_tiles <= 0 || n_chunks <= 0)
         return cudaSuccess;
@@ -183,7 +190,7 @@ cudaError_t launch_diff_euclid(const void *cells, const void *lib, float *D, uns
         return e;
     const unsigned grid = (unsigned)n_cell_tiles * (unsigned)n_lib_tiles;  // 1-D, super-block rasterisation (kernels.h)
     diff_euclid_kernel<<<grid, kEThreads, smem, stream>>>((const unsigned char *)cells, (const unsigned char *)lib, D, best_key, n_chunks,
-                                                          n_lib, n_lib_tiles * MM_ETN, n_cells, n_cell_tiles, n_lib_tiles);
+                                                          n_lib, n_lib_tiles * MM_ETN, n_cells, n_cell_tiles, n_lib_tiles, cancel, progress);
     return cudaGetLastError();
 }
 

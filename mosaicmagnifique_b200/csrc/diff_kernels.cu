@@ -81,11 +81,12 @@ template <int DIFF>
 __global__ void __launch_bounds__(kThreads, MM_MIN_CTAS)
 diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__restrict__ lib, float *__restrict__ D,
                 unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells,
-                int n_cell_tiles, int n_lib_tiles)
+                int n_cell_tiles, int n_lib_tiles, const int *__restrict__ cancel, unsigned long long *__restrict__ progress)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_bar[kStages];
     __shared__ uint64_t empty_bar[kStages];
+    __shared__ int s_cancelled;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int cell_tile, lib_tile;
@@ -97,8 +98,11 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
             mbar_init(&empty_bar[s], kConsumerWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_cancelled = cancel ? load_cancel_flag(cancel) : 0;
     }
     __syncthreads();
+    if (s_cancelled)
+        return;  // cancel(): nothing has been issued yet, the whole CTA leaves
 
     if (warp == kConsumerWarps) {
         // ---------------- producer warp: one elected lane drives the TMA ring
@@ -185,11 +189,14 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
             atomicMin(best_key + cell, key);
         }
     }
+    if (progress && threadIdx.x == 0)
+        atomicAdd(progress, 1ull);  // consumer warp 0 has stored its results; an approximate "tiles done" count is all that is needed
 }
 
 template <int DIFF>
 static cudaError_t launch(const void *cells, const void *lib, float *D, unsigned long long *best_key, int n_cell_tiles,
-                          int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream)
+                          int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream, const int *cancel,
+                          unsigned long long *progress)
 {
     const size_t smem = (size_t)kStages * kStageBytes;
     // per device (context) attribute: set on every launch, it is cheap
@@ -199,18 +206,19 @@ static cudaError_t launch(const void *cells, const void *lib, float *D, unsigned
     const unsigned grid = (unsigned)n_cell_tiles * (unsigned)n_lib_tiles;  // 1-D, super-block rasterisation (kernels.h)
     diff_sum_kernel<DIFF><<<grid, kThreads, smem, stream>>>((const unsigned char *)cells, (const unsigned char *)lib, D,
                                                              best_key, n_chunks, n_lib, n_lib_tiles * MM_TNB, n_cells, n_cell_tiles,
-                                                             n_lib_tiles);
+                                                             n_lib_tiles, cancel, progress);
     return cudaGetLastError();
 }
 
 cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, float *D, unsigned long long *best_key,
-                            int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream)
+                            int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream,
+                            const int *cancel, unsigned long long *progress)
 {
     if (n_cell_tiles <= 0 || n_lib_tiles <= 0 || n_chunks <= 0)
         return cudaSuccess;
     if (diff_type != MM_DIFF_CIEDE2000)
         return cudaErrorInvalidValue;  // RGB Euclidean / CIE76 run diff_euclid_kernel (diff_euclid.cu)
-    return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream);
+    return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream, cancel, progress);
 }
 
 }  // namespace mm

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mosaic_b200.h"
@@ -110,6 +111,7 @@ struct StepPlan {
     std::vector<int> next_x;           // next valid column in the same row
     std::vector<int> row_first;        // per grid row: column of the first valid cell (cols if none)
     int64_t cell_begin = 0, cell_end = 0;  // this rank's block of valid cells
+    int64_t per_rank = 0;                  // rows every rank owns in the all-gathered candidate buffer (multiple of the cell tile)
     double pixel_diffs = 0, pixel_diffs_nominal = 0;
 };
 
@@ -123,10 +125,15 @@ struct mosaic_generator {
 
     // inputs
     int img_rows = 0, img_cols = 0;
+    int main_lo = 0, main_hi = 0;  // rows of the main image that are resident on the device (sharded handles upload a band)
     DevBuf d_main_u8;
     int64_t n_lib = 0;
     int lib_size = 0;
     DevBuf d_lib_u8;
+    // sharded setLibrary (mosaic_set_library_shard): the library is stored at lib_stored_size -- the cell size, or already the
+    // detail size of step 0 when detail != 100 % (each rank resized its own slice before the NVLink all-gather)
+    int lib_stored_size = 0;
+    int64_t lib_capacity = 0;
     int diff_type = MOSAIC_RGB_EUCLIDEAN;
     int scheme = MOSAIC_SCHEME_NONE;
     bool quirk_faithful = true;
@@ -140,7 +147,16 @@ struct mosaic_generator {
 
     mosaic_progress_fn progress_fn = nullptr;
     void *progress_user = nullptr;
-    std::atomic<bool> cancelled{false};
+    // cancel(): one int in MAPPED pinned host memory. mosaic_cancel() is a plain store (callable from any thread or from inside the
+    // progress callback); the difference kernels read it through its device alias when a CTA starts.
+    int *h_cancel = nullptr;
+    int *d_cancel = nullptr;
+    // progress(int) while a launch runs: device counter of finished CTAs, polled over a second stream into pinned memory
+    cudaStream_t poll_stream = nullptr;
+    DevBuf d_progress;
+    unsigned long long *h_progress = nullptr;
+
+    bool is_cancelled() const { return h_cancel && __atomic_load_n(h_cancel, __ATOMIC_RELAXED) != 0; }
 
     // products
     DevBuf d_lut;
@@ -327,8 +343,8 @@ void make_plans(G *g)
         p.ds = grp.detail_cells[s].size;
         // library size at this step: round(detail size) at step 0, round(0.5 * previous) afterwards
         // (PhotomosaicGeneratorBase.cpp:262, ImageUtility.cpp:97-98); must agree with the detail mask
-        if (s == 0)
-            lib_ds = (grp.detail != 1.0) ? p.ds : g->lib_size;
+        if (s == 0)  // (before a library is set -- mosaic_get_shard_rows -- it is taken to be at the cell size, as check_ready demands)
+            lib_ds = (grp.detail != 1.0) ? p.ds : (g->lib_size ? g->lib_size : grp.cells[0].size);
         else {
             if (lib_ds % 2 != 0)
                 throw Fail{MOSAIC_ERR_UNSUPPORTED, "odd library size at a size step (the reference indexes out of range here)"};
@@ -361,15 +377,36 @@ void make_plans(G *g)
                     p.next_x.push_back(gs.cols);
                 }
         }
-        // rank's block of cells: a contiguous raster range of the step's valid cells (grid rows, cut at cell granularity
-        // on whole cell tiles so that every rank launches the same number of CTAs +- 1 tile)
+        // rank's block of cells: a contiguous raster range of the step's valid cells, cut at cell granularity on whole cell
+        // tiles. Every rank owns the same number of rows `per` of the padded list (the last ranks may own fewer real cells), so
+        // that rank r's candidates land at row r * per of one all-gathered buffer without any size exchange.
         const int64_t n = (int64_t)p.cell_pos.size();
         const int tcb = tile_geom(g->diff_type == MOSAIC_CIEDE2000 ? kLayoutCiede : kLayoutEuclid).tcb;
         const int64_t n_tiles = (n + tcb - 1) / tcb;
-        auto cut = [&](int r) { return std::min<int64_t>(n, (n_tiles * r / g->world) * tcb); };
-        p.cell_begin = cut(g->rank);
-        p.cell_end = g->rank == g->world - 1 ? n : cut(g->rank + 1);
+        p.per_rank = std::max<int64_t>(1, (n_tiles + g->world - 1) / g->world) * tcb;
+        p.cell_begin = std::min<int64_t>(n, (int64_t)g->rank * p.per_rank);
+        p.cell_end = std::min<int64_t>(n, (int64_t)(g->rank + 1) * p.per_rank);
     }
+}
+
+// main-image rows [lo, hi) that this rank's cells (all size steps) read; whole rows, so that the hue rotation keeps OpenCV's
+// per-row SIMD / tail split
+void needed_rows(const G *g, int &row_lo, int &row_hi)
+{
+    row_lo = g->img_rows;
+    row_hi = 0;
+    for (size_t s = 0; s < g->plans.size(); ++s) {
+        const StepPlan &p = g->plans[s];
+        const Shape &normal = g->group.cells[s];
+        for (int64_t c = p.cell_begin; c < p.cell_end; ++c) {
+            const int pos = p.cell_pos[c];
+            const Rect r = rect_at(normal, pos % p.cols - kPadGrid, pos / p.cols - kPadGrid);
+            row_lo = std::min(row_lo, std::max(r.y, 0));
+            row_hi = std::max(row_hi, std::min(r.y + r.h, g->img_rows));
+        }
+    }
+    if (row_hi < row_lo)
+        row_lo = row_hi = 0;
 }
 
 // ------------------------------------------------------------------ the pipeline
@@ -437,21 +474,13 @@ void run_pipeline(G *g, bool candidates_only)
     DevBuf &d_main_f32 = g->ws.main_f32;
     const size_t n_main_px = (size_t)g->img_rows * g->img_cols;
     d_main_f32.alloc((size_t)V * n_main_px * 3 * sizeof(float), st);
-    // a sharded rank only reads the image rows its own cells cover: convert just those (whole rows, so the hue rotation
-    // keeps OpenCV's per-row SIMD / tail split)
-    int row_lo = g->img_rows, row_hi = 0;
-    for (size_t s = 0; s < n_steps; ++s) {
-        const StepPlan &p = g->plans[s];
-        const Shape &normal = g->group.cells[s];
-        for (int64_t c = p.cell_begin; c < p.cell_end; ++c) {
-            const int pos = p.cell_pos[c];
-            const Rect r = rect_at(normal, pos % p.cols - kPadGrid, pos / p.cols - kPadGrid);
-            row_lo = std::min(row_lo, std::max(r.y, 0));
-            row_hi = std::max(row_hi, std::min(r.y + r.h, g->img_rows));
-        }
-    }
-    if (row_hi < row_lo)
-        row_lo = row_hi = 0;
+    // a sharded rank only reads the image rows its own cells cover: convert just those
+    int row_lo, row_hi;
+    needed_rows(g, row_lo, row_hi);
+    if (row_lo < g->main_lo || row_hi > g->main_hi)
+        throw Fail{MOSAIC_ERR_NOT_READY, "main image rows " + std::to_string(row_lo) + ".." + std::to_string(row_hi) +
+                                             " are needed by this shard but only " + std::to_string(g->main_lo) + ".." +
+                                             std::to_string(g->main_hi) + " were uploaded (mosaic_set_main_image_rows)"};
     const int n_rows_conv = row_hi - row_lo;
     const size_t row_off_px = (size_t)row_lo * g->img_cols;
     for (int v = 0; v < V && n_rows_conv > 0; ++v) {
@@ -477,20 +506,29 @@ void run_pipeline(G *g, bool candidates_only)
         const uint8_t *src = g->d_lib_u8.as<uint8_t>();
         if (g->group.detail != 1.0) {
             lib_ds = g->plans[0].ds;
-            d_lib_small.alloc((size_t)N * lib_ds * lib_ds * 3, st);
-            if (g->lib_size % lib_ds == 0) {
-                CU(launch_area_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, g->lib_size / lib_ds, st));
+            if (g->lib_stored_size != g->lib_size) {
+                // sharded setLibrary already resized every slice to the detail size (mosaic_set_library_shard)
+                if (g->lib_stored_size != lib_ds)
+                    throw Fail{MOSAIC_ERR_NOT_READY, "the library was uploaded for another detail size: call mosaic_set_library_shard "
+                                                     "again after changing the cell group"};
             } else {
-                const AreaTab tab = upload_area_table(g, g->lib_size, lib_ds, tm);
-                CU(launch_area_general_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, lib_ds, tab, st));
+                d_lib_small.alloc((size_t)N * lib_ds * lib_ds * 3, st);
+                if (g->lib_size % lib_ds == 0) {
+                    CU(launch_area_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, g->lib_size / lib_ds, st));
+                } else {
+                    const AreaTab tab = upload_area_table(g, g->lib_size, lib_ds, tm);
+                    CU(launch_area_general_u8(src, d_lib_small.as<uint8_t>(), N, g->lib_size, lib_ds, tab, st));
+                }
+                tm.kernel_launches++;
+                src = d_lib_small.as<uint8_t>();
             }
-            tm.kernel_launches++;
-            src = d_lib_small.as<uint8_t>();
+        } else if (g->lib_stored_size != g->lib_size) {
+            throw Fail{MOSAIC_ERR_NOT_READY, "the library was uploaded at a detail size but the cell group now has detail 100 %"};
         }
-        // CIEDE2000 with a single size step: the Lab conversion is fused into the tile-packing kernel below (straight from
-        // the 8U library), the f32 working-space copy is only materialised when a later step has to halve it
+        // a single size step: the colour conversion is fused into the tile-packing kernel below (straight from the 8U
+        // library), the f32 working-space copy is only materialised when a later step has to halve it
         lib_u8_at_ds = src;
-        fuse_lib_conversion = layout == kLayoutCiede && n_steps == 1;
+        fuse_lib_conversion = n_steps == 1;
         if (!fuse_lib_conversion) {
             d_lib_work.alloc((size_t)N * lib_ds * lib_ds * 3 * sizeof(float), st);
             // the library is one tall image of N * ds rows
@@ -519,10 +557,22 @@ void run_pipeline(G *g, bool candidates_only)
 
     const bool penalise = g->repeat_range > 0 && g->repeat_addition != 0;
     int progress = 0;
+    // cancel(): polled by the host before every phase it enqueues and by every CTA of the difference kernels when it starts
+    // (the reference polls per step, row and cell, CPUPhotomosaicGenerator.cpp:52, 66, 73). Work already enqueued drains first.
+    auto check_cancel = [&]() {
+        if (g->is_cancelled()) {
+            cudaStreamSynchronize(st);
+            throw Fail{MOSAIC_ERR_CANCELLED, "cancelled"};
+        }
+    };
+    unsigned long long *d_tiles_done = nullptr;
+    if (g->progress_fn) {
+        g->d_progress.alloc(sizeof(unsigned long long), st);
+        d_tiles_done = g->d_progress.as<unsigned long long>();
+    }
 
     for (size_t s = 0; s < n_steps; ++s) {
-        if (g->cancelled.load())
-            throw Fail{MOSAIC_ERR_CANCELLED, "cancelled"};
+        check_cancel();
         StepPlan &p = g->plans[s];
         const Shape &normal = g->group.cells[s];
         const Shape &dshape = g->group.detail_cells[s];
@@ -540,13 +590,22 @@ void run_pipeline(G *g, bool candidates_only)
             std::swap(d_lib_work, half);
         }
 
-        // active pixel list: union of the four flipped detail masks, raster order
+        // active pixel list: union of the flipped detail masks THAT OCCUR among the step's valid cells (all ranks' cells, so that
+        // every world size sums in the same order), raster order. A shape without flips (Puzzle.mcs) keeps its own 72 % of the
+        // square instead of the ~100 % the union of all four flips would cover.
         const std::vector<uint8_t> m4 = dshape.masks4();
+        bool flip_used[4] = {false, false, false, false};
+        for (int pos : p.cell_pos)
+            flip_used[flip_at(normal, pos % p.cols - kPadGrid, pos / p.cols - kPadGrid)] = true;
         std::vector<int> pix;
         pix.reserve(P);
-        for (int i = 0; i < P; ++i)
-            if (m4[i] | m4[(size_t)P + i] | m4[(size_t)2 * P + i] | m4[(size_t)3 * P + i])
+        for (int i = 0; i < P; ++i) {
+            bool on = false;
+            for (int f = 0; f < 4; ++f)
+                on = on || (flip_used[f] && m4[(size_t)f * P + i]);
+            if (on)
                 pix.push_back(i);
+        }
         p.n_active = (int)pix.size();
         p.n_chunks = std::max(1, (p.n_active + tg.kp - 1) / tg.kp);
         d.pix_list.alloc(std::max<size_t>(pix.size(), 1) * sizeof(int), st);
@@ -557,9 +616,12 @@ void run_pipeline(G *g, bool candidates_only)
 
         // library tiles
         d.lib_packed.alloc((size_t)n_lib_tiles * p.n_chunks * tg.lib_block, st);
-        if (fuse_lib_conversion)
+        if (fuse_lib_conversion && layout == kLayoutCiede)
             CU(launch_pack_library_ciede(lib_u8_at_ds, true, d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
                                          n_lib_tiles, g->d_lut.as<short4>(), st));
+        else if (fuse_lib_conversion)
+            CU(launch_pack_library_euclid_u8(lib_u8_at_ds, is_lab, d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active,
+                                             p.n_chunks, n_lib_tiles, g->d_lut.as<short4>(), st));
         else
             CU(launch_pack_library(d_lib_work.as<float>(), d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
                                    n_lib_tiles, layout, st));
@@ -624,17 +686,45 @@ void run_pipeline(G *g, bool candidates_only)
             CU(launch_fill_u64(d.best_key.as<unsigned long long>(), (size_t)std::max(n_rows_pad, 1), ~0ull, st));
             tm.kernel_launches++;
         }
+        check_cancel();
+        if (d_tiles_done)
+            CU(cudaMemsetAsync(d_tiles_done, 0, sizeof(unsigned long long), st));
         if (layout == kLayoutCiede)
             CU(launch_diff_sum(MM_DIFF_CIEDE2000, d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
                                fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
-                               (int)N, n_rows_local, st));
+                               (int)N, n_rows_local, st, g->d_cancel, d_tiles_done));
         else
             CU(launch_diff_euclid(d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
                                   fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
-                                  (int)N, n_rows_local, st));
+                                  (int)N, n_rows_local, st, g->d_cancel, d_tiles_done));
         if (n_cell_tiles > 0)
             tm.kernel_launches++;
         clock.end();
+        const int step_weight = (int)pow(4.0, (double)(n_steps - 1 - s));
+        const int positions = p.rows * p.cols;
+        if (g->progress_fn) {
+            // the host watches the launch from here (before anything that could block it, e.g. the pageable D2H copy of the grid)
+            cudaEvent_t done;
+            CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+            cudaEventRecord(done, st);
+            const unsigned long long total = (unsigned long long)std::max(n_cell_tiles, 1) * (unsigned long long)n_lib_tiles;
+            int last = progress;
+            while (cudaEventQuery(done) == cudaErrorNotReady) {
+                if (cudaMemcpyAsync(g->h_progress, d_tiles_done, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->poll_stream) == cudaSuccess &&
+                    cudaStreamSynchronize(g->poll_stream) == cudaSuccess && !g->is_cancelled()) {
+                    const unsigned long long dn = std::min(*g->h_progress, total);
+                    const int v = progress + step_weight * (int)((unsigned long long)positions * dn / total);
+                    if (v > last && v < progress + step_weight * positions) {
+                        last = v;
+                        g->progress_fn(v, g->progress_user);  // may call mosaic_cancel(): the running kernel then drains
+                    }
+                }
+                std::this_thread::sleep_for(std::chrono::microseconds(500));
+            }
+            cudaEventDestroy(done);
+            cudaGetLastError();
+            check_cancel();
+        }
 
         // ---- Repeats + FindLowest
         clock.begin(kSel);
@@ -648,10 +738,13 @@ void run_pipeline(G *g, bool candidates_only)
             const int64_t kk = penalise ? std::min<int64_t>(N, 2 * r * r + 2 * r + 1) : 1;
             const int K = (int)kk;
             g->cand_k[s] = K;
-            g->d_cand_score[s].alloc((size_t)std::max<int64_t>(n_local, 1) * K * sizeof(float), st);
-            g->d_cand_idx[s].alloc((size_t)std::max<int64_t>(n_local, 1) * K * sizeof(int), st);
-            CU(launch_topk(D.as<float>(), V * n_lib_pad, (int)N, (int)n_local, K, g->d_cand_score[s].as<float>(),
-                           g->d_cand_idx[s].as<int>(), st));
+            // one block per rank: float scores [per_rank][K] followed by int32 indices [per_rank][K]; every rank's block has the
+            // same size, so ONE all-gather assembles the candidates of the whole step (rank r's rows start at r * per_rank)
+            const size_t half = (size_t)p.per_rank * K;
+            g->d_cand_score[s].alloc(half * (sizeof(float) + sizeof(int)), st);
+            float *cs = g->d_cand_score[s].as<float>();
+            int *ci = reinterpret_cast<int *>(cs + half);
+            CU(launch_topk(D.as<float>(), V * n_lib_pad, (int)N, (int)n_local, K, cs, ci, st));
             if (n_local > 0)
                 tm.kernel_launches++;
         } else {
@@ -706,15 +799,20 @@ void run_pipeline(G *g, bool candidates_only)
             tm.d2h_bytes += (double)(gs.v.size() * sizeof(long long));
         }
         clock.end();
-        // progress(int): the reference emits per cell with weight 4^(steps-1-step) (CPUPhotomosaicGenerator.cpp:55, 87-88);
-        // here once per finished size step (the only point where the host waits inside the pipeline, and only if asked)
-        progress += (int)(pow(4.0, (double)(n_steps - 1 - s)) * p.rows * p.cols);
-        if (g->progress_fn) {
+        // progress(int): the reference emits after every grid position, cumulative, with weight 4^(steps-1-step)
+        // (CPUPhotomosaicGenerator.cpp:55, 87-88). Here the host polls the device's count of finished difference tiles while the
+        // step runs and emits base + weight * floor(positions * done / total): every emitted value is one the reference emits too,
+        // the sequence is increasing and each step ends on the reference's own step total. Only when a callback is installed --
+        // otherwise the pipeline never waits on the host before its final synchronise.
+        if (g->progress_fn) {  // the step's own total: the value the reference reaches after the step's last grid position
             CU(cudaStreamSynchronize(st));
-            g->progress_fn(progress, g->progress_user);
+            check_cancel();
+            g->progress_fn(progress + step_weight * positions, g->progress_user);
         }
+        progress += step_weight * positions;
     }
     CU(cudaStreamSynchronize(st));
+    check_cancel();
     tm.preprocess_ms = clock.sum(kPre);
     tm.diff_ms = clock.sum(kDiff);
     tm.select_ms = clock.sum(kSel);
@@ -747,6 +845,15 @@ int mosaic_create(int device, mosaic_generator **out)
         delete g;
         return MOSAIC_ERR_CUDA;
     }
+    if (cudaStreamCreateWithFlags(&g->poll_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void **)&g->h_cancel, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&g->d_cancel, g->h_cancel, 0) != cudaSuccess ||
+        cudaHostAlloc((void **)&g->h_progress, sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) {
+        mosaic_destroy(g);
+        return MOSAIC_ERR_CUDA;
+    }
+    *g->h_cancel = 0;
+    *g->h_progress = 0;
     cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -772,10 +879,17 @@ void mosaic_destroy(mosaic_generator *g)
     g->d_cand_score.clear();
     g->d_cand_idx.clear();
     g->d_margins.clear();
+    g->d_progress.release();
     if (g->stream) {
         cudaStreamSynchronize(g->stream);
         cudaStreamDestroy(g->stream);
     }
+    if (g->poll_stream)
+        cudaStreamDestroy(g->poll_stream);
+    if (g->h_cancel)
+        cudaFreeHost(g->h_cancel);
+    if (g->h_progress)
+        cudaFreeHost(g->h_progress);
     delete g;
 }
 
@@ -800,6 +914,53 @@ int mosaic_set_main_image(mosaic_generator *g, const uint8_t *bgr, int rows, int
 
         g->img_rows = a.rows;
         g->img_cols = a.cols;
+        g->main_lo = 0;
+        g->main_hi = a.rows;
+    }, &a);
+}
+
+int mosaic_get_shard_rows(mosaic_generator *g, int rows, int cols, int *row_lo, int *row_hi)
+{
+    struct A {
+        int rows, cols, *lo, *hi;
+    } a{rows, cols, row_lo, row_hi};
+    return guard(g, "getShardRows", [](G *g, void *p) {
+        A &a = *(A *)p;
+        if (a.rows <= 0 || a.cols <= 0 || !a.lo || !a.hi)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "image size and output pointers are required"};
+        if (!g->have_group || g->grid.empty())
+            throw Fail{MOSAIC_ERR_NOT_READY, "cell group and grid state must be set first"};
+        if (a.rows != g->img_rows || a.cols != g->img_cols) {
+            g->img_rows = a.rows;  // the image is declared; no row is resident yet
+            g->img_cols = a.cols;
+            g->main_lo = g->main_hi = 0;
+        }
+        make_plans(g);
+        needed_rows(g, *a.lo, *a.hi);
+    }, &a);
+}
+
+int mosaic_set_main_image_rows(mosaic_generator *g, const uint8_t *bgr, int rows, int cols, size_t row_stride, int row_lo, int row_hi)
+{
+    struct A {
+        const uint8_t *bgr;
+        int rows, cols;
+        size_t stride;
+        int lo, hi;
+    } a{bgr, rows, cols, row_stride, row_lo, row_hi};
+    return guard(g, "setMainImageRows", [](G *g, void *p) {
+        A &a = *(A *)p;
+        if (!a.bgr || a.rows <= 0 || a.cols <= 0 || a.stride < (size_t)a.cols * 3 || a.lo < 0 || a.hi > a.rows || a.lo > a.hi)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "main image must be a non-empty 8U BGR image and 0 <= row_lo <= row_hi <= rows"};
+        g->d_main_u8.alloc((size_t)a.rows * a.cols * 3, g->stream);  // full-size buffer: row indices stay global
+        if (a.hi > a.lo)
+            CU(cudaMemcpy2DAsync(g->d_main_u8.as<uint8_t>() + (size_t)a.lo * a.cols * 3, (size_t)a.cols * 3, a.bgr + (size_t)a.lo * a.stride,
+                                 a.stride, (size_t)a.cols * 3, (size_t)(a.hi - a.lo), cudaMemcpyDefault, g->stream));
+        CU(cudaStreamSynchronize(g->stream));
+        g->img_rows = a.rows;
+        g->img_cols = a.cols;
+        g->main_lo = a.lo;
+        g->main_hi = a.hi;
     }, &a);
 }
 
@@ -821,7 +982,70 @@ int mosaic_set_library(mosaic_generator *g, const uint8_t *bgr, int64_t n, int s
         CU(cudaStreamSynchronize(g->stream));
         g->n_lib = a.n;
         g->lib_size = a.size;
+        g->lib_stored_size = a.size;
+        g->lib_capacity = a.n;
     }, &a);
+}
+
+int mosaic_set_library_shard(mosaic_generator *g, const uint8_t *bgr_slice, int64_t first, int64_t count, int64_t n_total, int size,
+                             int64_t capacity_images)
+{
+    struct A {
+        const uint8_t *bgr;
+        int64_t first, count, n, cap;
+        int size;
+    } a{bgr_slice, first, count, n_total, capacity_images, size};
+    return guard(g, "setLibraryShard", [](G *g, void *p) {
+        A &a = *(A *)p;
+        if (a.n <= 0 || a.size <= 0 || a.first < 0 || a.count < 0 || a.first + a.count > a.n || a.cap < a.n || (a.count > 0 && !a.bgr))
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "need 0 <= first, first + count <= n_total <= capacity and a slice pointer"};
+        if (a.n * a.size > INT32_MAX)
+            throw Fail{MOSAIC_ERR_UNSUPPORTED, "library too large (n * size must fit 31 bits)"};
+        if (!g->have_group)
+            throw Fail{MOSAIC_ERR_NOT_READY, "the cell group must be set first (its detail level decides the stored size)"};
+        if (a.size != g->group.cells[0].size)
+            throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "library images must be at the cell size"};
+        cudaStream_t st = g->stream;
+        // stored size: the detail size of step 0 when the generator would resize anyway (PhotomosaicGeneratorBase.cpp:262-270)
+        const int ds = g->group.detail != 1.0 ? g->group.detail_cells[0].size : a.size;
+        const size_t stored_img = (size_t)ds * ds * 3, full_img = (size_t)a.size * a.size * 3;
+        g->d_lib_u8.alloc((size_t)a.cap * stored_img, st);
+        uint8_t *dst = g->d_lib_u8.as<uint8_t>() + (size_t)a.first * stored_img;
+        if (a.count > 0) {
+            if (ds == a.size) {
+                CU(cudaMemcpyAsync(dst, a.bgr, (size_t)a.count * full_img, cudaMemcpyDefault, st));
+            } else {
+                DevBuf &stage = g->ws.lib_small;  // full-size slice, resized on the GPU into its place
+                stage.alloc((size_t)a.count * full_img, st);
+                CU(cudaMemcpyAsync(stage.p, a.bgr, (size_t)a.count * full_img, cudaMemcpyDefault, st));
+                if (a.size % ds == 0) {
+                    CU(launch_area_u8(stage.as<uint8_t>(), dst, a.count, a.size, a.size / ds, st));
+                } else {
+                    mosaic_timings scratch{};
+                    const AreaTab tab = upload_area_table(g, a.size, ds, scratch);
+                    CU(launch_area_general_u8(stage.as<uint8_t>(), dst, a.count, a.size, ds, tab, st));
+                }
+            }
+        }
+        CU(cudaStreamSynchronize(st));
+        g->n_lib = a.n;
+        g->lib_size = a.size;
+        g->lib_stored_size = ds;
+        g->lib_capacity = a.cap;
+    }, &a);
+}
+
+int mosaic_get_library_device(const mosaic_generator *g, void **ptr, int *stored_size, int64_t *capacity_images)
+{
+    if (!g || !g->d_lib_u8.p)
+        return MOSAIC_ERR_NOT_READY;
+    if (ptr)
+        *ptr = g->d_lib_u8.p;
+    if (stored_size)
+        *stored_size = g->lib_stored_size;
+    if (capacity_images)
+        *capacity_images = g->lib_capacity;
+    return MOSAIC_OK;
 }
 
 int mosaic_set_colour_difference(mosaic_generator *g, int type)
@@ -926,6 +1150,8 @@ int mosaic_compute_grid_state(mosaic_generator *g)
         try {
             if (cudaSetDevice(g->device) != cudaSuccess)
                 throw Fail{MOSAIC_ERR_CUDA, "cudaSetDevice failed"};
+            if (g->main_lo != 0 || g->main_hi != g->img_rows)
+                throw Fail{MOSAIC_ERR_NOT_READY, "the entropy rule needs the whole main image on the device (only a band of rows was uploaded)"};
             cudaStream_t st = g->stream;
             const Shape &dshape = g->group.detail_cells[step];
             const std::vector<uint8_t> m4 = dshape.masks4();
@@ -981,10 +1207,9 @@ int mosaic_generate(mosaic_generator *g)
 {
     if (g && g->world != 1)
         return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "generateBestFits: sharded handles use mosaic_generate_candidates + mosaic_select_from_candidates");
-    return guard(g, "generateBestFits", [](G *g, void *) {
-        g->cancelled.store(false);
-        run_pipeline(g, false);
-    }, nullptr);
+    // m_wasCanceled is never reset by the reference (PhotomosaicGeneratorBase.cpp:35, 219): a cancel() issued before the call
+    // makes it return at once; mosaic_reset_cancel() re-arms the handle
+    return guard(g, "generateBestFits", [](G *g, void *) { run_pipeline(g, false); }, nullptr);
 }
 
 int mosaic_get_best_fits(const mosaic_generator *g, int step, int64_t *out, int rows, int cols)
@@ -1016,8 +1241,14 @@ void mosaic_set_progress_callback(mosaic_generator *g, mosaic_progress_fn fn, vo
 
 void mosaic_cancel(mosaic_generator *g)
 {
-    if (g)
-        g->cancelled.store(true);
+    if (g && g->h_cancel)
+        __atomic_store_n(g->h_cancel, 1, __ATOMIC_RELAXED);
+}
+
+void mosaic_reset_cancel(mosaic_generator *g)
+{
+    if (g && g->h_cancel)
+        __atomic_store_n(g->h_cancel, 0, __ATOMIC_RELAXED);
 }
 
 int mosaic_set_keep_differences(mosaic_generator *g, int keep)
@@ -1111,6 +1342,9 @@ int mosaic_build_photomosaic(mosaic_generator *g, const uint8_t background_bgra[
             throw Fail{MOSAIC_ERR_NOT_READY, "no best fits to build from"};
         if (g->lib_size != g->group.cells[0].size)
             throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "library images must be at the cell size"};
+        if (g->lib_stored_size != g->lib_size)
+            throw Fail{MOSAIC_ERR_NOT_READY, "buildPhotomosaic needs the library at the cell size (it was uploaded at the detail size "
+                                             "by mosaic_set_library_shard)"};
         cudaStream_t st = g->stream;
         const int H = g->img_rows, W = g->img_cols, n_steps = (int)g->grid.size();
         const int64_t N = g->n_lib;
@@ -1195,10 +1429,7 @@ int mosaic_set_shard(mosaic_generator *g, int rank, int world)
 
 int mosaic_generate_candidates(mosaic_generator *g)
 {
-    return guard(g, "generateCandidates", [](G *g, void *) {
-        g->cancelled.store(false);
-        run_pipeline(g, true);
-    }, nullptr);
+    return guard(g, "generateCandidates", [](G *g, void *) { run_pipeline(g, true); }, nullptr);
 }
 
 int mosaic_get_candidate_count(const mosaic_generator *g, int step, int64_t *first_cell, int64_t *n_cells, int *k)
@@ -1216,23 +1447,44 @@ int mosaic_get_candidate_count(const mosaic_generator *g, int step, int64_t *fir
 
 int mosaic_get_candidates_device(const mosaic_generator *g, int step, void **scores, void **indices)
 {
-    if (!g || step < 0 || step >= (int)g->d_cand_score.size() || !scores || !indices)
+    if (!g || step < 0 || step >= (int)g->d_cand_score.size() || step >= (int)g->plans.size() || step >= (int)g->cand_k.size() ||
+        !scores || !indices)
         return MOSAIC_ERR_NOT_READY;
-    *scores = g->d_cand_score[step].p;
-    *indices = g->d_cand_idx[step].p;
+    float *cs = g->d_cand_score[step].as<float>();
+    *scores = cs;
+    *indices = cs ? (void *)(cs + (size_t)g->plans[step].per_rank * g->cand_k[step]) : nullptr;
     return MOSAIC_OK;
 }
 
-int mosaic_select_from_candidates(mosaic_generator *g, int step, const void *scores, const void *indices, int k)
+int mosaic_get_candidate_block(const mosaic_generator *g, int step, void **block, int64_t *rows_per_rank, int *k, size_t *block_bytes)
+{
+    if (!g || step < 0 || step >= (int)g->d_cand_score.size() || step >= (int)g->plans.size() || step >= (int)g->cand_k.size())
+        return MOSAIC_ERR_NOT_READY;
+    if (block)
+        *block = g->d_cand_score[step].p;
+    if (rows_per_rank)
+        *rows_per_rank = g->plans[step].per_rank;
+    if (k)
+        *k = g->cand_k[step];
+    if (block_bytes)
+        *block_bytes = (size_t)g->plans[step].per_rank * g->cand_k[step] * (sizeof(float) + sizeof(int));
+    return MOSAIC_OK;
+}
+
+namespace {
+// selection over the candidates of ALL cells of a step. rows_per_block == 0: scores / indices are plain [n_valid][k] arrays;
+// otherwise `scores` is the all-gathered buffer of per-rank blocks {float [rows_per_block][k], int32 [rows_per_block][k]}.
+int select_impl(mosaic_generator *g, int step, const void *scores, const void *indices, int k, int64_t rows_per_block)
 {
     struct A {
         int step;
         const void *scores, *indices;
         int k;
-    } a{step, scores, indices, k};
+        int64_t rpb;
+    } a{step, scores, indices, k, rows_per_block};
     return guard(g, "selectFromCandidates", [](G *g, void *ap) {
         A &a = *(A *)ap;
-        if (a.step < 0 || a.step >= (int)g->plans.size() || !a.scores || !a.indices || a.k < 1)
+        if (a.step < 0 || a.step >= (int)g->plans.size() || !a.scores || (!a.indices && a.rpb == 0) || a.k < 1)
             throw Fail{MOSAIC_ERR_INVALID_ARGUMENT, "bad step or candidate buffers"};
         StepPlan &p = g->plans[a.step];
         GridStep &gs = g->grid[a.step];
@@ -1252,11 +1504,18 @@ int mosaic_select_from_candidates(mosaic_generator *g, int step, const void *sco
         const int n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(n_all, select_max_ctas(g->device)));
         d_counts.alloc((size_t)n_ctas * g->n_lib * sizeof(int), st);
         CU(cudaMemsetAsync(d_counts.p, 0, d_counts.bytes, st));
+        const float *sc = (const float *)a.scores;
+        const int *ix = (const int *)a.indices;
+        int64_t block_stride = 0;
+        if (a.rpb > 0) {
+            ix = reinterpret_cast<const int *>(sc + (size_t)a.rpb * a.k);  // indices follow the scores inside every block
+            block_stride = 2 * a.rpb * a.k;                                 // in 4-byte elements
+        }
         Timer t(st);
         t.start();
-        CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols, (const float *)a.scores,
-                         (const int *)a.indices, a.k, a.k, (int)g->n_lib, g->repeat_range, g->repeat_addition, d_prog.as<int>(),
-                         d_counts.as<int>(), n_ctas, nullptr, st));
+        CU(launch_select(d_grid.as<long long>(), d_pos.as<int>(), d_next.as<int>(), (int)n_all, p.rows, p.cols, sc, ix, a.k, a.k,
+                         (int)g->n_lib, g->repeat_range, g->repeat_addition, d_prog.as<int>(), d_counts.as<int>(), n_ctas, nullptr,
+                         st, a.rpb, block_stride));
         t.stop();
         CU(cudaMemcpyAsync(gs.v.data(), d_grid.p, gs.v.size() * sizeof(long long), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -1264,6 +1523,19 @@ int mosaic_select_from_candidates(mosaic_generator *g, int step, const void *sco
         g->timings.kernel_launches += n_all > 0;
         g->timings.d2h_bytes += (double)(gs.v.size() * sizeof(long long));
     }, &a);
+}
+}  // namespace
+
+int mosaic_select_from_candidates(mosaic_generator *g, int step, const void *scores, const void *indices, int k)
+{
+    return select_impl(g, step, scores, indices, k, 0);
+}
+
+int mosaic_select_from_gathered(mosaic_generator *g, int step, const void *gathered_blocks, int k, int64_t rows_per_rank)
+{
+    if (g && rows_per_rank <= 0)
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "selectFromGathered: rows_per_rank must be positive");
+    return select_impl(g, step, gathered_blocks, nullptr, k, rows_per_rank);
 }
 
 // ---- host geometry

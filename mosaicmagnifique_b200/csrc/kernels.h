@@ -39,6 +39,13 @@ namespace mm {
 // 842 GB of DRAM reads for config 4 instead of ~95 GB (profiles/r1_diff_sum_ciede2000_final_cfg4.txt).
 constexpr int kSuperTiles = 16;
 #if defined(__CUDACC__)
+// system-scope load of the cancel flag (mapped host memory: must not be served from a stale cache line)
+__device__ __forceinline__ int load_cancel_flag(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void tile_of_block(unsigned id, int n_ct, int n_lt, int &cell_tile, int &lib_tile)
 {
     const unsigned band_ctas = (unsigned)n_ct * kSuperTiles;  // CTAs of one full band of kSuperTiles library tiles
@@ -67,12 +74,18 @@ inline TileGeom tile_geom(PackLayout l)
 }
 
 // ---- diff_euclid.cu
+// cancel   : optional device-visible flag (mapped pinned host memory); a CTA that finds it set at its start returns at once, so a
+//            cancelled launch drains in the time the remaining CTAs take to be scheduled (CPUPhotomosaicGenerator.cpp:52-73 polls
+//            m_wasCanceled per cell)
+// progress : optional device counter, +1 per finished CTA (progress(int) reporting while the launch runs)
 cudaError_t launch_diff_euclid(const void *cells, const void *lib, float *D, unsigned long long *best_key, int n_cell_tiles,
-                               int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream);
+                               int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream,
+                               const int *cancel = nullptr, unsigned long long *progress = nullptr);
 
 // ---- diff_kernels.cu
 cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, float *D, unsigned long long *best_key,
-                            int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream);
+                            int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream,
+                            const int *cancel = nullptr, unsigned long long *progress = nullptr);
 
 // ---- prep_kernels.cu
 // u8 BGR -> working space f32 AoS [pixel][3]: Lab through the OpenCV-compatible LUT (is_lab) or a plain cast.
@@ -120,6 +133,11 @@ cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P
 // the f32 working-space library; padding slots are written by the same pass
 cudaError_t launch_pack_library_ciede(const void *src, bool src_is_u8, void *packed, int64_t n, int P, const int *pix_list,
                                       int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream);
+
+// Euclidean layout straight from the 8U BGR library at the detail size (plain cast, or the Lab conversion for CIE76, fused);
+// padding slots are written by the same pass
+cudaError_t launch_pack_library_euclid_u8(const uint8_t *lib, bool is_lab, void *packed, int64_t n, int P, const int *pix_list,
+                                          int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream);
 
 struct CellDesc {
     int x0, y0;          // top-left of the (unclipped) cell rect in main-image space
@@ -174,10 +192,11 @@ cudaError_t launch_topk(const float *D, int row_stride, int n_lib, int n_cells, 
 //   row_progress : [rows] initialised to the column of the first valid cell of each row (cols if none)
 //   counts       : [n_ctas][n_lib] zero-filled scratch
 //   margins      : optional [n_cells][2] best / second-best penalised score of every cell
+//   rows_per_block / block_stride : candidate lists all-gathered from several GPUs (see SelArgs); 0 = one plain array
 cudaError_t launch_select(long long *grid, const int *cell_pos, const int *next_x, int n_cells, int rows, int cols,
                           const float *scores, const int *idx, int M, int M_stride, int n_lib, int repeat_range,
                           int repeat_addition, int *row_progress, int *counts, int n_ctas, float *margins,
-                          cudaStream_t stream);
+                          cudaStream_t stream, long long rows_per_block = 0, long long block_stride = 0);
 int select_max_ctas(int device);
 // best_key (from the diff epilogue) -> grid
 cudaError_t launch_keys_to_grid(const unsigned long long *best_key, const int *cell_pos, long long *grid, int n_cells,

@@ -379,6 +379,67 @@ __global__ void pack_library_euclid_kernel(const float *__restrict__ lib, unsign
     }
 }
 
+// Euclidean layout straight from the 8U BGR library at the detail size: one CTA per (library tile, chunk) block of
+// 16 pixels x 64 images. Loads run along the pixels of one image (pix_list is raster order, so 16 slots are mostly 48 contiguous
+// bytes), the conversion (plain cast for RGB, OpenCV's Lab LUT for CIE76 -- lab_from_bgr8, same arithmetic as
+// to_working_space_kernel) is fused in, the block is transposed through shared memory and leaves as one coalesced 12 KB write with
+// its padding slots zeroed: the f32 working-space copy of the library (0.98 GB written and read again at config 5) and the memset
+// of the packed tensor are gone. Used when there is a single size step (with size steps the f32 copy feeds the per-step halving).
+constexpr int kEuclidRow = 3 * MM_ETN + 1;  // padded pixel stride of the staging tile (bank spread of the transposing writes)
+template <bool kLab>
+__global__ void __launch_bounds__(256)
+pack_library_euclid_u8_kernel(const uint8_t *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
+                              const int *__restrict__ pix_list, int n_active, int n_chunks, size_t n_blocks,
+                              const short4 *__restrict__ lut)
+{
+    __shared__ float s[MM_EKP * kEuclidRow];
+    for (size_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const size_t tile = blk / n_chunks;
+        const int chunk = (int)(blk - tile * n_chunks);
+        for (int item = threadIdx.x; item < MM_EKP * MM_ETN; item += 256) {
+            const int pi = item % MM_EKP, ti = item / MM_EKP;
+            const int q = chunk * MM_EKP + pi;
+            const int64_t im = (int64_t)tile * MM_ETN + ti;
+            float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
+            if (q < n_active && im < n) {
+                const uint8_t *s8 = lib + ((size_t)im * P + pix_list[q]) * 3;
+                if (kLab) {
+                    lab_from_bgr8(s8[0], s8[1], s8[2], lut, v0, v1, v2);
+                } else {
+                    v0 = (float)s8[0];
+                    v1 = (float)s8[1];
+                    v2 = (float)s8[2];
+                }
+            }
+            float *d = s + pi * kEuclidRow + ti;  // library values are stored NEGATED (cell - lib becomes a packed add)
+            d[0] = -v0;
+            d[MM_ETN] = -v1;
+            d[2 * MM_ETN] = -v2;
+        }
+        __syncthreads();
+        float *out = reinterpret_cast<float *>(packed + blk * (size_t)(MM_EKP * 3 * MM_ETN * 4));
+        for (int j = threadIdx.x; j < MM_EKP * 3 * MM_ETN; j += 256)
+            out[j] = s[(j / (3 * MM_ETN)) * kEuclidRow + j % (3 * MM_ETN)];
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_pack_library_euclid_u8(const uint8_t *lib, bool is_lab, void *packed, int64_t n, int P, const int *pix_list,
+                                          int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream)
+{
+    const size_t n_blocks = (size_t)n_lib_tiles * n_chunks;
+    if (n_blocks == 0)
+        return cudaSuccess;
+    const int grid = (int)(n_blocks < 148 * 16 ? n_blocks : 148 * 16);
+    if (is_lab)
+        pack_library_euclid_u8_kernel<true><<<grid, 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active, n_chunks,
+                                                                      n_blocks, lab_lut);
+    else
+        pack_library_euclid_u8_kernel<false><<<grid, 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active, n_chunks,
+                                                                       n_blocks, lab_lut);
+    return cudaGetLastError();
+}
+
 // CIEDE2000 layout, one thread per (image PAIR slot, pixel slot) of the padded tile grid: two complete float4 stores per
 // thread (consecutive threads = consecutive pixels -> fully coalesced), padding slots written as zeros by the same pass
 // (no separate memset of the 2.6 GB tensor). kFromU8: the source is the 8U BGR library at the detail size and the Lab

@@ -197,6 +197,9 @@ struct SelArgs {
     int *row_progress;     // [rows], initialised to the column of the first valid cell (cols if none)
     int *counts;           // [gridDim.x][n_lib] zeroed scratch: occurrences of each library image in the window
     float *margins;        // optional [n_cells][2]: best and second-best PENALISED score (tie-band reporting)
+    // all-gathered candidate blocks (multi-GPU): cell c lives in block c / rows_per_block at row c % rows_per_block; blocks are
+    // block_stride 4-byte elements apart (scores and indices alike). rows_per_block == 0: one plain array.
+    long long rows_per_block, block_stride;
 };
 
 __device__ __forceinline__ int ld_acquire(const int *p)
@@ -258,8 +261,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelArgs a)
         __syncthreads();
 
         // ---- penalised argmin over this cell's entries
-        const float *sc = a.scores + (size_t)c * a.M_stride;
-        const int *ids = a.idx ? a.idx + (size_t)c * a.M : nullptr;
+        size_t row = (size_t)c, base = 0;
+        if (a.rows_per_block > 0) {
+            base = (size_t)(c / a.rows_per_block) * (size_t)a.block_stride;
+            row = (size_t)(c % a.rows_per_block);
+        }
+        const float *sc = a.scores + base + row * a.M_stride;
+        const int *ids = a.idx ? a.idx + base + row * a.M : nullptr;
         double best = DBL_MAX, second = DBL_MAX;
         int best_id = 0x7fffffff;
         for (int j = tid; j < a.M; j += kSelThreads) {
@@ -338,12 +346,12 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelArgs a)
 cudaError_t launch_select(long long *grid, const int *cell_pos, const int *next_x, int n_cells, int rows, int cols,
                           const float *scores, const int *idx, int M, int M_stride, int n_lib, int repeat_range,
                           int repeat_addition, int *row_progress, int *counts, int n_ctas, float *margins,
-                          cudaStream_t stream)
+                          cudaStream_t stream, long long rows_per_block, long long block_stride)
 {
     if (n_cells == 0)
         return cudaSuccess;
     SelArgs a{grid, cell_pos, next_x, n_cells, rows, cols, scores, idx, M, M_stride, n_lib, repeat_range, repeat_addition,
-              row_progress, counts, margins};
+              row_progress, counts, margins, rows_per_block, block_stride};
     void *args[] = {&a};
     // cooperative launch: fails instead of deadlocking if the CTAs could not all be resident
     return cudaLaunchCooperativeKernel((void *)select_kernel, dim3(n_ctas), dim3(kSelThreads), args, 0, stream);

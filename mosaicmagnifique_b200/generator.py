@@ -312,7 +312,11 @@ class PhotomosaicGenerator:
         self._L.mosaic_set_progress_callback(self._h, self._progress_cb, None)
 
     def cancel(self):
+        """slot cancel(): sticky like m_wasCanceled -- generateBestFits() returns False until resetCancel()."""
         self._L.mosaic_cancel(self._h)
+
+    def resetCancel(self):
+        self._L.mosaic_reset_cancel(self._h)
 
     # ---- parity / measurement taps
     def setKeepDifferences(self, keep: bool = True):
@@ -358,3 +362,37 @@ class PhotomosaicGenerator:
 
     def selectFromCandidates(self, step: int, scores_ptr: int, indices_ptr: int, k: int):
         self._ck(self._L.mosaic_select_from_candidates(self._h, step, scores_ptr, indices_ptr, k))
+
+    def candidateBlock(self, step: int):
+        """This rank's candidates of a step as ONE device block {f32 scores [rows_per_rank][k], i32 indices [rows_per_rank][k]};
+        every rank's block has the same size, so a single all-gather assembles the step (parallel.generate_sharded)."""
+        ptr, rows, k, nbytes = ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_size_t()
+        self._ck(self._L.mosaic_get_candidate_block(self._h, step, ctypes.byref(ptr), ctypes.byref(rows), ctypes.byref(k),
+                                                    ctypes.byref(nbytes)))
+        return {"ptr": ptr.value, "rows_per_rank": rows.value, "k": k.value, "bytes": nbytes.value,
+                "n_valid": self._L.mosaic_get_valid_cell_count(self._h, step)}
+
+    def selectFromGathered(self, step: int, gathered_ptr: int, k: int, rows_per_rank: int):
+        self._ck(self._L.mosaic_select_from_gathered(self._h, step, gathered_ptr, k, rows_per_rank))
+
+    # ---- sharded inputs: a rank uploads only what it computes on
+    def shardRows(self, rows: int, cols: int):
+        """Main-image rows [lo, hi) this handle's cells read (cell group, grid state and shard set beforehand)."""
+        lo, hi = ctypes.c_int(), ctypes.c_int()
+        self._ck(self._L.mosaic_get_shard_rows(self._h, rows, cols, ctypes.byref(lo), ctypes.byref(hi)))
+        return lo.value, hi.value
+
+    def setMainImageRowsPtr(self, ptr: int, rows: int, cols: int, row_stride: int, row_lo: int, row_hi: int):
+        """setMainImage from a pointer to row 0 of the full image, uploading rows [row_lo, row_hi) only."""
+        self._main_shape = (rows, cols)
+        self._ck(self._L.mosaic_set_main_image_rows(self._h, ptr, rows, cols, row_stride, row_lo, row_hi))
+
+    def setLibraryShardPtr(self, slice_ptr: int, first: int, count: int, n_total: int, size: int, capacity: int):
+        """This rank's slice of the library (resized to the detail size on the GPU when detail != 100 %)."""
+        self._n_lib = n_total
+        self._ck(self._L.mosaic_set_library_shard(self._h, slice_ptr, first, count, n_total, size, capacity))
+
+    def libraryDevice(self):
+        ptr, stored, cap = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int64()
+        self._ck(self._L.mosaic_get_library_device(self._h, ctypes.byref(ptr), ctypes.byref(stored), ctypes.byref(cap)))
+        return {"ptr": ptr.value, "stored_size": stored.value, "capacity": cap.value}

@@ -87,8 +87,26 @@ cv::Mat cv::imdecode(const std::vector<uchar> &buf, int)
     return m;
 }
 
-// ---- the moc-generated signal body
-void PhotomosaicGeneratorBase::progress(const int t_progressStep) { g_progress.push_back(t_progressStep); }
+// ---- the moc-generated signal body. A QProgressDialog connected to the signal calls the generator's cancel() slot from inside
+// the emission when the user presses Cancel (MainWindow.cpp:597-603); ref_cancel_after(n) plays that user at the n-th emission.
+static int g_cancel_after = 0;
+void PhotomosaicGeneratorBase::progress(const int t_progressStep)
+{
+    g_progress.push_back(t_progressStep);
+    if (g_cancel_after > 0 && (int)g_progress.size() == g_cancel_after)
+        cancel();
+}
+extern "C" {
+void ref_cancel_after(int n_emissions) { g_cancel_after = n_emissions; }
+void ref_progress_clear(void) { g_progress.clear(); }
+int ref_progress_get(int *out, int cap)
+{
+    const int n = (int)g_progress.size();
+    for (int i = 0; i < n && i < cap; ++i)
+        out[i] = g_progress[i];
+    return n;
+}
+}
 
 namespace {
 struct Runner : public CPUPhotomosaicGenerator {

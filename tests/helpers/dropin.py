@@ -42,3 +42,21 @@ def run(oracle, backend, main, lib, group, grid_states, diff, scheme, rr, ra, ba
     if rc < 0:
         raise RuntimeError("dropin_run failed (%d)" % rc)
     return rc, grids, mosaic
+
+
+def cancel_after(oracle, n_emissions: int):
+    """Plays the user pressing Cancel at the n-th progress(int) emission (0 = never): the signal body of the harness calls the
+    generator's own cancel() slot, as a connected QProgressDialog does."""
+    oracle._ref().ref_cancel_after(int(n_emissions))
+
+
+def progress_values(oracle):
+    R = oracle._ref()
+    n = R.ref_progress_get(None, 0)
+    buf = (ctypes.c_int * max(n, 1))()
+    R.ref_progress_get(buf, n)
+    return list(buf[:n])
+
+
+def progress_clear(oracle):
+    oracle._ref().ref_progress_clear()

@@ -41,6 +41,34 @@ def test_b200_backend_equals_reference_cpu_backend(oracle, case):
     else:
         want = oracle.generate(main, lib, group, states, diff, 0, rr, ra, want_D=True)
         for s in range(len(states)):
-            _, ties, bad = check_grid(want[s].D, states[s], b200_grids[s], rr, ra, 1e-4)
+            _, ties, bad = check_grid(want[s].D, states[s], b200_grids[s], rr, ra)
             assert not bad, bad[:3]
     print("%s: grids %s" % (case, "identical, mosaics identical" if same else "equal outside the tie band"))
+
+
+def test_cancel_slot_is_honoured_by_the_b200_backend(oracle):
+    """the binding ignored cancel(). The user cancels from the progress dialog, i.e. the cancel() slot runs inside
+    a progress(int) emission: both back-ends must then return false from generateBestFits() -- the reference's CPU back-end at its
+    next per-cell check, the B200 back-end by draining its kernel."""
+    if not (oracle.reference_generator_available() and dropin.available()):
+        pytest.skip("oracle/_ref/libdropin_b200.so not present / not loadable")
+    from mosaicmagnifique_b200 import synthetic
+    main = synthetic.make_main_image(2160, 3840, 931)
+    lib = synthetic.make_library(2500, 64, 932)
+    group = oracle.CellGroup.make(oracle.CellShape.square(64), 100, 0)
+    states = oracle.reference_grid_state(group, main)
+    try:
+        for backend in (0, 1):
+            dropin.progress_clear(oracle)
+            dropin.cancel_after(oracle, 2)
+            rc, _, _ = dropin.run(oracle, backend, main, lib, group, states, 2, 0, 2, 300, want_mosaic=False)
+            seen = dropin.progress_values(oracle)
+            assert rc == 1, "backend %d ignored cancel()" % backend
+            assert 2 <= len(seen) < states[0].size and seen[-1] < states[0].size, (backend, len(seen))
+    finally:
+        dropin.cancel_after(oracle, 0)
+    # and without a cancel the B200 back-end still completes and reports the reference's final progress value
+    dropin.progress_clear(oracle)
+    rc, grids, _ = dropin.run(oracle, 1, main, lib, group, states, 2, 0, 2, 300, want_mosaic=False)
+    seen = dropin.progress_values(oracle)
+    assert rc == 0 and seen[-1] == states[0].size and (grids[0][states[0] >= 0] >= 0).all()

@@ -1,16 +1,17 @@
 """End-to-end parity of the generator on the GPU against the CPU oracle, through the reference-shaped API.
 Option matrix follows the reference's generator tests (test/tst_Generator.h:145-439, tst_CUDAGenerator.h:226-823):
 {RGB, CIE76, CIEDE2000} x {detail 100, 50}, repeats, size steps, a non-square cell shape with flips, edge cells.
-Criterion: grid equality outside the tie band (helpers/parity.py), difference sums within 1e-4 relative."""
+Criterion: grid equality outside the tie band (helpers/parity.py: 1e-5 relative, what FP32 can explain), difference sums within
+2e-5 relative (BASELINE.json asks for 1e-4)."""
 import os
 
 import numpy as np
 import pytest
 
-from tests.helpers.parity import check_grid, rel_err
+from tests.helpers.parity import D_TOL, TIE_TOL, check_grid, rel_err
 
 pytestmark = pytest.mark.gpu
-TOL = 1e-4  # BASELINE.json: per-cell difference values within 1e-4 relative; same number bounds the tie band
+TOL = TIE_TOL  # grid criterion: a cell may differ only if its two candidates are within the FP32-explainable band (1e-5)
 
 
 def _inputs(seed, h, w, n_lib, cell):
@@ -68,7 +69,7 @@ def _run_case(oracle, main, lib, o_shape, diff, detail, steps, rr, ra, use_oracl
         assert D.shape == w.D.shape
         if D.size:
             e = rel_err(D, w.D)
-            assert e.max() < TOL, "step %d: max relative error of the difference sums %.3g" % (step, e.max())
+            assert e.max() < D_TOL, "step %d: max relative error of the difference sums %.3g" % (step, e.max())
         n, t, bad = check_grid(w.D, states[step], g, rr, ra, TOL)
         assert not bad, "step %d: %d cells differ outside the tie band, first %s" % (step, len(bad), bad[:3])
         total += n
@@ -247,7 +248,7 @@ def test_build_photomosaic(oracle, hexa, steps, detail):
 @pytest.mark.parametrize("name", ["square_ciede2000", "triangle_rgb", "hexagon_cie76"])
 def test_generator_matches_committed_golden(oracle, name):
     """The CUDA path against the COMMITTED fixtures of tests/golden/generator_golden.npz (inputs and oracle outputs written
-    by tests/golden/make_generator_golden.py in the build container): difference sums within 1e-4 relative, grid states
+    by tests/golden/make_generator_golden.py in the build container): difference sums within 2e-5 relative, grid states
     identical, grids identical outside the tie band. No oracle run is involved, only its recorded numbers."""
     from mosaicmagnifique_b200 import CellGroup, PhotomosaicGenerator
     from tests.test_oracle_pipeline import _golden, golden_case
@@ -275,7 +276,7 @@ def test_generator_matches_committed_golden(oracle, name):
         D = gen.getDifferences(s)
         assert D.shape == D_want.shape
         if D.size:
-            assert rel_err(D, D_want).max() < TOL
+            assert rel_err(D, D_want).max() < D_TOL
         n, ties, bad = check_grid(D_want, states[s], got[s], rr, ra, TOL)
         assert not bad, bad[:3]
         # outside the tie band the recorded oracle grid is reproduced exactly
@@ -368,7 +369,7 @@ def test_all_cells_invalid_and_single_valid_cell(oracle):
     og = oracle.CellGroup.make(oracle.CellShape.square(32), 100, 0)
     want = oracle.generate(main, lib, og, one, 2, 0, 2, 100, want_D=True)[0]
     assert g[3, 3] == want.grid[3, 3]
-    assert rel_err(gen.getDifferences(0), want.D).max() < TOL
+    assert rel_err(gen.getDifferences(0), want.D).max() < D_TOL
     gen.close()
 
 
@@ -378,7 +379,7 @@ def test_all_cells_invalid_and_single_valid_cell(oracle):
 def test_cuda_path_against_reference_object_code(oracle, case):
     """The CUDA path against the reference's OWN generator (PhotomosaicGeneratorBase.cpp + CPUPhotomosaicGenerator.cpp +
     GridGenerator.cpp compiled unmodified into oracle/_ref/libref_core.so, which travels to the GPU box prebuilt): grid
-    states identical; best-fit grids identical except inside the tie band (cells whose penalised f64 score is within 1e-4
+    states identical; best-fit grids identical except inside the tie band (cells whose penalised f64 score is within 1e-5
     relative of the best, given the cells already chosen -- tests/helpers/parity.py)."""
     if not oracle.reference_generator_available():
         pytest.skip("oracle/_ref/libref_core.so (reference object code) not present / not loadable")
