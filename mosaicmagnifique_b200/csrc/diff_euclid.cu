@@ -61,7 +61,7 @@ __device__ __forceinline__ void bulk_g2s_e(void *dst, const void *src, uint32_t 
                  : "memory");
 }
 
-constexpr int kEStages = 3;
+constexpr int kEStages = MM_ESTAGES;
 constexpr int kEConsumerWarps = 8;
 constexpr int kEThreads = (kEConsumerWarps + 1) * 32;
 constexpr uint32_t kECellBlock = MM_EKP * 4 * MM_ETC * 4;  // [pixel][x0,x1,x2,w][64 cells] f32
@@ -87,12 +87,13 @@ diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char 
     tile_of_block(blockIdx.x, n_cell_tiles, n_lib_tiles, cell_tile, lib_tile);
 
     if (threadIdx.x == 0) {
+        const int cancelled = cancel ? load_cancel_flag(cancel) : 0;  // device word (L2 hit), in flight during the barrier set-up
         for (int s = 0; s < kEStages; ++s) {
             mbar_init_e(&full_bar[s], 1);
             mbar_init_e(&empty_bar[s], kEConsumerWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_cancelled = cancel ? load_cancel_flag(cancel) : 0;
+        s_cancelled = cancelled;
     }
     __syncthreads();
     if (s_cancelled)
@@ -107,6 +108,8 @@ diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char 
                 if (k >= kEStages)
                     mbar_wait_e(&empty_bar[s], ((k / kEStages) - 1) & 1);
                 unsigned char *dst = smem + (size_t)s * kEStage;
+                if (MM_STRESS_SKEW)
+                    __nanosleep((unsigned)((k * 131 + blockIdx.x * 17) % 300));
                 mbar_expect_tx_e(&full_bar[s], kEStage);
                 bulk_g2s_e(dst, cell_src + (size_t)k * kECellBlock, kECellBlock, &full_bar[s]);
                 bulk_g2s_e(dst + kECellBlock, lib_src + (size_t)k * kELibBlock, kELibBlock, &full_bar[s]);
@@ -126,6 +129,8 @@ diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char 
     for (int k = 0; k < n_chunks; ++k) {
         const int s = k % kEStages;
         mbar_wait_e(&full_bar[s], (k / kEStages) & 1);
+        if (MM_STRESS_SKEW)
+            __nanosleep((unsigned)((warp * 97 + k * 29 + blockIdx.x * 7) % 400));
         const float4 *cs = reinterpret_cast<const float4 *>(smem + (size_t)s * kEStage) + tc;
         const float4 *ls = reinterpret_cast<const float4 *>(smem + (size_t)s * kEStage + kECellBlock) + tl;
 #pragma unroll 2

@@ -93,12 +93,13 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
     tile_of_block(blockIdx.x, n_cell_tiles, n_lib_tiles, cell_tile, lib_tile);
 
     if (threadIdx.x == 0) {
+        const int cancelled = cancel ? load_cancel_flag(cancel) : 0;  // device word (L2 hit), in flight during the barrier set-up
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kConsumerWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_cancelled = cancel ? load_cancel_flag(cancel) : 0;
+        s_cancelled = cancelled;
     }
     __syncthreads();
     if (s_cancelled)
@@ -114,6 +115,8 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
                 if (k >= kStages)
                     mbar_wait(&empty_bar[s], ((k / kStages) - 1) & 1);
                 unsigned char *dst = smem + (size_t)s * kStageBytes;
+                if (MM_STRESS_SKEW)
+                    __nanosleep((unsigned)((k * 131 + blockIdx.x * 17) % 300));
                 mbar_expect_tx(&full_bar[s], kStageBytes);
                 bulk_g2s(dst, lib_src + (size_t)k * kLibBlockBytes, kLibBlockBytes, &full_bar[s]);
                 bulk_g2s(dst + kLibBlockBytes, cell_src + (size_t)k * kCellBlockBytes, kCellBlockBytes, &full_bar[s]);
@@ -131,6 +134,8 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
     for (int k = 0; k < n_chunks; ++k) {
         const int s = k % kStages;
         mbar_wait(&full_bar[s], (k / kStages) & 1);
+        if (MM_STRESS_SKEW)
+            __nanosleep((unsigned)((warp * 97 + k * 29 + blockIdx.x * 7) % 400));
         const float4 *lib_s = reinterpret_cast<const float4 *>(smem + (size_t)s * kStageBytes);
         const float4 *cell_s = reinterpret_cast<const float4 *>(smem + (size_t)s * kStageBytes + kLibBlockBytes) + warp * MM_KP;
         const float *w_s = reinterpret_cast<const float *>(smem + (size_t)s * kStageBytes + kLibBlockBytes + MM_TCB * MM_KP * 16) + warp * MM_KP;

@@ -147,10 +147,13 @@ struct mosaic_generator {
 
     mosaic_progress_fn progress_fn = nullptr;
     void *progress_user = nullptr;
-    // cancel(): one int in MAPPED pinned host memory. mosaic_cancel() is a plain store (callable from any thread or from inside the
-    // progress callback); the difference kernels read it through its device alias when a CTA starts.
+    // cancel(): a flag in pinned host memory (what the host tests) mirrored into a word of DEVICE memory by a 4-byte DMA on the
+    // poll stream; every CTA of the difference kernels reads the device word (an L2 hit) when it starts. (Reading mapped host
+    // memory from every CTA was measured first: 296 CTAs polling one PCIe address cost 25 % of the kernel and made a cancelled
+    // launch drain no faster than a complete one.)
     int *h_cancel = nullptr;
     int *d_cancel = nullptr;
+    bool cancel_pushed = false;  // the device word already holds 1 (generate thread only)
     // progress(int) while a launch runs: device counter of finished CTAs, polled over a second stream into pinned memory
     cudaStream_t poll_stream = nullptr;
     DevBuf d_progress;
@@ -200,6 +203,8 @@ int guard(G *g, const char *what, void (*fn)(G *, void *), void *arg)
         return g->fail(MOSAIC_ERR_OUT_OF_MEMORY, std::string(what) + ": host allocation failed");
     } catch (const std::exception &e) {
         return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, std::string(what) + ": " + e.what());
+    } catch (...) {
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, std::string(what) + ": unexpected failure");
     }
 }
 
@@ -309,6 +314,28 @@ struct Timer {
         return m;
     }
 };
+
+// ------------------------------------------------------------------ cancel plumbing
+
+// copies a raised host flag into the device word (once per generate call)
+void push_cancel(G *g)
+{
+    if (!g->cancel_pushed && g->is_cancelled()) {
+        cudaMemcpyAsync(g->d_cancel, g->h_cancel, sizeof(int), cudaMemcpyHostToDevice, g->poll_stream);
+        g->cancel_pushed = true;
+    }
+}
+
+// cudaStreamSynchronize that keeps an eye on cancel(): spins on the stream like the runtime's own wait does, and forwards a
+// cancel raised meanwhile to the device so that the running kernel stops scheduling work
+void wait_stream(G *g, cudaStream_t st)
+{
+    cudaError_t e;
+    while ((e = cudaStreamQuery(st)) == cudaErrorNotReady)
+        push_cancel(g);
+    if (e != cudaSuccess)
+        throw Fail{MOSAIC_ERR_CUDA, std::string("stream wait: ") + cudaGetErrorString(e)};
+}
 
 // ------------------------------------------------------------------ planning
 
@@ -429,6 +456,8 @@ AreaTab upload_area_table(G *g, int ssize, int dsize, mosaic_timings &tm)
 void run_pipeline(G *g, bool candidates_only)
 {
     check_ready(g);
+    if (g->is_cancelled())  // sticky like m_wasCanceled (never reset by the reference): nothing runs until mosaic_reset_cancel
+        throw Fail{MOSAIC_ERR_CANCELLED, "cancelled"};
     make_plans(g);
     cudaStream_t st = g->stream;
     const auto t_host0 = std::chrono::steady_clock::now();
@@ -561,10 +590,15 @@ void run_pipeline(G *g, bool candidates_only)
     // (the reference polls per step, row and cell, CPUPhotomosaicGenerator.cpp:52, 66, 73). Work already enqueued drains first.
     auto check_cancel = [&]() {
         if (g->is_cancelled()) {
+            push_cancel(g);
             cudaStreamSynchronize(st);
             throw Fail{MOSAIC_ERR_CANCELLED, "cancelled"};
         }
     };
+    check_cancel();  // sticky like m_wasCanceled: a cancelled handle does nothing until mosaic_reset_cancel
+    g->cancel_pushed = false;
+    CU(cudaStreamSynchronize(g->poll_stream));                     // no stale flag copy may land after the reset below
+    CU(cudaMemsetAsync(g->d_cancel, 0, sizeof(int), st));
     unsigned long long *d_tiles_done = nullptr;
     if (g->progress_fn) {
         g->d_progress.alloc(sizeof(unsigned long long), st);
@@ -719,6 +753,7 @@ void run_pipeline(G *g, bool candidates_only)
                         g->progress_fn(v, g->progress_user);  // may call mosaic_cancel(): the running kernel then drains
                     }
                 }
+                push_cancel(g);
                 std::this_thread::sleep_for(std::chrono::microseconds(500));
             }
             cudaEventDestroy(done);
@@ -805,13 +840,13 @@ void run_pipeline(G *g, bool candidates_only)
         // the sequence is increasing and each step ends on the reference's own step total. Only when a callback is installed --
         // otherwise the pipeline never waits on the host before its final synchronise.
         if (g->progress_fn) {  // the step's own total: the value the reference reaches after the step's last grid position
-            CU(cudaStreamSynchronize(st));
+            wait_stream(g, st);
             check_cancel();
             g->progress_fn(progress + step_weight * positions, g->progress_user);
         }
         progress += step_weight * positions;
     }
-    CU(cudaStreamSynchronize(st));
+    wait_stream(g, st);
     check_cancel();
     tm.preprocess_ms = clock.sum(kPre);
     tm.diff_ms = clock.sum(kDiff);
@@ -846,8 +881,8 @@ int mosaic_create(int device, mosaic_generator **out)
         return MOSAIC_ERR_CUDA;
     }
     if (cudaStreamCreateWithFlags(&g->poll_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaHostAlloc((void **)&g->h_cancel, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
-        cudaHostGetDevicePointer((void **)&g->d_cancel, g->h_cancel, 0) != cudaSuccess ||
+        cudaHostAlloc((void **)&g->h_cancel, sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc((void **)&g->d_cancel, 256) != cudaSuccess || cudaMemset(g->d_cancel, 0, 256) != cudaSuccess ||
         cudaHostAlloc((void **)&g->h_progress, sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) {
         mosaic_destroy(g);
         return MOSAIC_ERR_CUDA;
@@ -888,6 +923,8 @@ void mosaic_destroy(mosaic_generator *g)
         cudaStreamDestroy(g->poll_stream);
     if (g->h_cancel)
         cudaFreeHost(g->h_cancel);
+    if (g->d_cancel)
+        cudaFree(g->d_cancel);
     if (g->h_progress)
         cudaFreeHost(g->h_progress);
     delete g;
@@ -1102,6 +1139,8 @@ int mosaic_set_cell_group(mosaic_generator *g, const mosaic_cell_shape *shape, c
         return MOSAIC_OK;
     } catch (const std::bad_alloc &) {
         return g->fail(MOSAIC_ERR_OUT_OF_MEMORY, "setCellGroup: host allocation failed");
+    } catch (...) {
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setCellGroup: unexpected failure");
     }
 }
 
@@ -1125,15 +1164,23 @@ int mosaic_set_grid_state(mosaic_generator *g, int step, int rows, int cols, con
         return MOSAIC_ERR_INVALID_ARGUMENT;
     if (!valid || step < 0 || rows <= 0 || cols <= 0 || step > (int)g->grid.size())
         return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setGridState: steps must be set in order with a rows x cols validity map");
-    if (step == (int)g->grid.size())
-        g->grid.emplace_back();
-    GridStep &gs = g->grid[step];
-    gs.rows = rows;
-    gs.cols = cols;
-    gs.v.resize((size_t)rows * cols);
-    for (size_t i = 0; i < gs.v.size(); ++i)
-        gs.v[i] = valid[i] ? 0 : -1;  // valid cells start as 0 (GridGenerator.cpp:192)
-    g->grid.resize(step + 1);
+    // no exception may cross the C ABI: the grid vectors are the only host allocation whose size the caller controls
+    if ((int64_t)rows * cols > ((int64_t)1 << 28))
+        return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setGridState: rows * cols is implausibly large (> 2^28 cells)");
+    try {
+        if (step == (int)g->grid.size())
+            g->grid.emplace_back();
+        GridStep &gs = g->grid[step];
+        gs.rows = rows;
+        gs.cols = cols;
+        gs.v.resize((size_t)rows * cols);
+        for (size_t i = 0; i < gs.v.size(); ++i)
+            gs.v[i] = valid[i] ? 0 : -1;  // valid cells start as 0 (GridGenerator.cpp:192)
+        g->grid.resize(step + 1);
+    } catch (...) {
+        g->grid.clear();
+        return g->fail(MOSAIC_ERR_OUT_OF_MEMORY, "setGridState: host allocation failed");
+    }
     return MOSAIC_OK;
 }
 
@@ -1241,8 +1288,18 @@ void mosaic_set_progress_callback(mosaic_generator *g, mosaic_progress_fn fn, vo
 
 void mosaic_cancel(mosaic_generator *g)
 {
-    if (g && g->h_cancel)
-        __atomic_store_n(g->h_cancel, 1, __ATOMIC_RELAXED);
+    if (!g || !g->h_cancel)
+        return;
+    __atomic_store_n(g->h_cancel, 1, __ATOMIC_RELAXED);
+    // mirror it into the device word right away (the generate thread does the same from its wait loops, so a failure here --
+    // e.g. a calling thread that cannot touch the device -- only delays the kernel's reaction by one poll)
+    int prev = -1;
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(g->device) == cudaSuccess) {
+        cudaMemcpyAsync(g->d_cancel, g->h_cancel, sizeof(int), cudaMemcpyHostToDevice, g->poll_stream);
+        if (prev >= 0 && prev != g->device)
+            cudaSetDevice(prev);
+    }
+    cudaGetLastError();
 }
 
 void mosaic_reset_cancel(mosaic_generator *g)
@@ -1542,6 +1599,8 @@ int mosaic_select_from_gathered(mosaic_generator *g, int step, const void *gathe
 
 void mosaic_grid_size(const mosaic_cell_shape *shape, int image_w, int image_h, int pad, int *grid_w, int *grid_h)
 {
+    if (!shape || !grid_w || !grid_h)
+        return;
     int gx = 0, gy = 0;
     grid_size(shape_params_only(*shape), image_w, image_h, pad, gx, gy);
     *grid_w = gx;
@@ -1550,6 +1609,8 @@ void mosaic_grid_size(const mosaic_cell_shape *shape, int image_w, int image_h, 
 
 void mosaic_rect_at(const mosaic_cell_shape *shape, int x, int y, int rect_xywh[4])
 {
+    if (!shape || !rect_xywh)
+        return;
     const Rect r = rect_at(shape_params_only(*shape), x, y);
     rect_xywh[0] = r.x;
     rect_xywh[1] = r.y;
@@ -1557,7 +1618,10 @@ void mosaic_rect_at(const mosaic_cell_shape *shape, int x, int y, int rect_xywh[
     rect_xywh[3] = r.h;
 }
 
-int mosaic_flip_at(const mosaic_cell_shape *shape, int x, int y) { return flip_at(shape_params_only(*shape), x, y); }
+int mosaic_flip_at(const mosaic_cell_shape *shape, int x, int y)
+{
+    return shape ? flip_at(shape_params_only(*shape), x, y) : MOSAIC_ERR_INVALID_ARGUMENT;
+}
 
 int mosaic_host_grid_state(const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size, int detail_percent, int size_steps,
                            const uint8_t *bgr, int rows, int cols, size_t row_stride, int max_steps, int *n_steps, int *step_rows,
@@ -1597,6 +1661,8 @@ int mosaic_host_grid_state(const mosaic_cell_shape *shape, const uint8_t *mask, 
         return MOSAIC_OK;
     } catch (const std::bad_alloc &) {
         return MOSAIC_ERR_OUT_OF_MEMORY;
+    } catch (...) {
+        return MOSAIC_ERR_INVALID_ARGUMENT;
     }
 }
 

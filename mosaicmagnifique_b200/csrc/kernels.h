@@ -20,6 +20,14 @@
 #ifndef MM_STAGES
 #define MM_STAGES 3  // shared-memory ring depth of the difference kernel
 #endif
+#ifndef MM_ESTAGES
+#define MM_ESTAGES 3  // ring depth of the Euclidean kernel
+#endif
+// MM_STRESS_SKEW=1 (stress build only, `make stress`): consumer warps and the producer lane sleep pseudo-random amounts per
+// chunk, so that the warps of a CTA drift apart by more than the ring depth would allow if the full/empty protocol had a hole
+#ifndef MM_STRESS_SKEW
+#define MM_STRESS_SKEW 0
+#endif
 #ifndef MM_MIN_CTAS
 #define MM_MIN_CTAS 2  // __launch_bounds__ residency target of the difference kernel
 #endif
@@ -39,7 +47,8 @@ namespace mm {
 // 842 GB of DRAM reads for config 4 instead of ~95 GB (profiles/r1_diff_sum_ciede2000_final_cfg4.txt).
 constexpr int kSuperTiles = 16;
 #if defined(__CUDACC__)
-// system-scope load of the cancel flag (mapped host memory: must not be served from a stale cache line)
+// strong system-scope load of the cancel word: it is written by the copy engine while the kernel runs, so it must come from L2
+// (the point of coherence for device memory), never from a stale L1 line
 __device__ __forceinline__ int load_cancel_flag(const int *p)
 {
     int v;
@@ -74,7 +83,7 @@ inline TileGeom tile_geom(PackLayout l)
 }
 
 // ---- diff_euclid.cu
-// cancel   : optional device-visible flag (mapped pinned host memory); a CTA that finds it set at its start returns at once, so a
+// cancel   : optional flag word in device memory (the host mirrors cancel() into it by DMA); a CTA that finds it set at its start returns at once, so a
 //            cancelled launch drains in the time the remaining CTAs take to be scheduled (CPUPhotomosaicGenerator.cpp:52-73 polls
 //            m_wasCanceled per cell)
 // progress : optional device counter, +1 per finished CTA (progress(int) reporting while the launch runs)

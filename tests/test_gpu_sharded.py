@@ -157,6 +157,7 @@ def test_missing_rows_are_reported():
     main = synthetic.make_main_image(200, 260, 5, block=32)
     lib = synthetic.make_library(20, 32, 6)
     g = PhotomosaicGenerator(0)
+    g.setColourDifference(2)  # CIEDE2000 layout: cell tiles of 8, so rank 1 of 2 owns the lower half of this small grid
     cg = CellGroup()
     cg.setCellShape(CellShape(32))
     g.setCellGroup(cg)
