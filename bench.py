@@ -641,7 +641,7 @@ def main():
                "phases_ms_per_step": head["phases_ms_per_step"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
                "clocks": m["clocks"], "roofline": head["roofline"],
                "microbench": {"ffma_lane_ops_per_s": mb[0], "ffma2_lane_ops_per_s": mb[1], "mufu_rsq_per_s": mb[2], "mufu_ex2_per_s": mb[3],
-                              "sm_count": int(mb[4]), "ciede_mix_pairs_per_s": mb[6]}}
+                              "sm_count": int(mb[4]), "ciede_mix_pairs_per_s": mb[6], "ffma2_plus_ffma_lane_ops_per_s": [mb[9], mb[10]]}}
         if tie is not None:
             out["tie_band"] = tie
         if cpu is not None:

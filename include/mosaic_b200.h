@@ -214,7 +214,8 @@ int mosaic_library_ingest(int device, const uint8_t *bgr, int rows, int cols, si
 /* FP32 / MUFU pipe-rate micro-benchmark (roofline denominators): out[0] FFMA lane-ops/s, [1] FFMA2 lane-ops/s,
  * [2] MUFU.RSQ ops/s, [3] MUFU.EX2 ops/s, [4] SM count, [5] cycles per 16-FFMA loop iteration, and (n_out >= 9) the rate of a
  * synthetic loop in the CIEDE2000 kernel's instruction proportions, in "pixel pairs"/s: [6] 40 FFMA2 + 9 MUFU + 5 ALU,
- * [7] 40 FFMA2 + 9 MUFU, [8] 40 FFMA2 */
+ * [7] 40 FFMA2 + 9 MUFU, [8] 40 FFMA2; (n_out >= 11) FP32 lane-ops/s of a loop mixing packed and scalar FMAs:
+ * [9] 8 FFMA2 + 8 FFMA, [10] 8 FFMA2 + 16 FFMA per iteration */
 int mosaic_kernel_microbench(int device, double *out, int n_out);
 
 /* ---- host-side geometry (no GPU needed): GridUtility.cpp:25-52, 86-132; CellShape::resized */

@@ -121,10 +121,14 @@ diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char 
     // consumer thread -> 4 cells x 4 images of the 64 x 64 tile
     const int tc = threadIdx.x & 15;   // cells 4*tc .. 4*tc+3
     const int tl = threadIdx.x >> 4;   // images 4*tl .. 4*tl+3
-    mm_f2 acc[4][2];
+    // Two-level accumulation: `acc` collects kFlushChunks chunks (1,024 pixels), then moves into `tot`. One FP32 accumulator per
+    // pair over a whole 256 px cell (65,536 terms of ~150 into a sum of 1e7, ulp 1) drifted by up to 3e-5 relative; in two
+    // levels every addition happens at <= 1/64 of that magnitude and the error stays near 1e-6 (tests/test_gpu_ring_stress.py).
+    constexpr int kFlushChunks = 64;
+    mm_f2 acc[4][2], tot[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        acc[i][0] = acc[i][1] = mm_f2{0.0f, 0.0f};
+        acc[i][0] = acc[i][1] = tot[i][0] = tot[i][1] = mm_f2{0.0f, 0.0f};
 
     for (int k = 0; k < n_chunks; ++k) {
         const int s = k % kEStages;
@@ -154,7 +158,21 @@ diff_euclid_kernel(const unsigned char *__restrict__ cells, const unsigned char 
         __syncwarp();
         if (lane == 0)
             mbar_arrive_e(&empty_bar[s]);
+        if ((k % kFlushChunks) == kFlushChunks - 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int cp = 0; cp < 2; ++cp) {
+                    tot[i][cp] = v_add(tot[i][cp], acc[i][cp]);
+                    acc[i][cp] = mm_f2{0.0f, 0.0f};
+                }
+        }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int cp = 0; cp < 2; ++cp)
+            acc[i][cp] = v_add(tot[i][cp], acc[i][cp]);
 
     // epilogue: every thread owns complete sums of its 4 x 4 block
     const int li0 = lib_tile * MM_ETN + tl * 4;

@@ -23,6 +23,9 @@
 // keeps TNB running sums, reduced with warp shuffles at the end. Roofline: FP32 + MUFU issue.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "colour_math.cuh"
 #include "kernels.h"
@@ -81,7 +84,8 @@ template <int DIFF>
 __global__ void __launch_bounds__(kThreads, MM_MIN_CTAS)
 diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__restrict__ lib, float *__restrict__ D,
                 unsigned long long *__restrict__ best_key, int n_chunks, int n_lib, int n_lib_pad, int n_cells,
-                int n_cell_tiles, int n_lib_tiles, const int *__restrict__ cancel, unsigned long long *__restrict__ progress)
+                int n_cell_tiles, int n_lib_tiles, const int *__restrict__ cancel, unsigned long long *__restrict__ progress,
+                int nk, int sb_a, int sb_b)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_bar[kStages];
@@ -90,7 +94,19 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int cell_tile, lib_tile;
-    tile_of_block(blockIdx.x, n_cell_tiles, n_lib_tiles, cell_tile, lib_tile);
+    {
+        // super-block raster (kernels.h: Raster): keep a column of sb_a cell tiles and sweep the library in bands of sb_b tiles
+        const unsigned id = blockIdx.x;
+        const unsigned col_all = (unsigned)sb_a * (unsigned)n_lib_tiles;
+        const unsigned cb = id / col_all;
+        const unsigned r = id - cb * col_all;
+        const int cw = min(sb_a, n_cell_tiles - (int)cb * sb_a);
+        const unsigned band_ctas = (unsigned)cw * (unsigned)sb_b;
+        const unsigned band = r / band_ctas;
+        const unsigned r2 = r - band * band_ctas;
+        cell_tile = (int)cb * sb_a + (int)(r2 % cw);
+        lib_tile = (int)band * sb_b + (int)(r2 / cw);
+    }
 
     if (threadIdx.x == 0) {
         const int cancelled = cancel ? load_cancel_flag(cancel) : 0;  // device word (L2 hit), in flight during the barrier set-up
@@ -110,7 +126,7 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
         if (lane == 0) {
             const unsigned char *cell_src = cells + (size_t)cell_tile * n_chunks * kCellBlockBytes;
             const unsigned char *lib_src = lib + (size_t)lib_tile * n_chunks * kLibBlockBytes;
-            for (int k = 0; k < n_chunks; ++k) {
+            for (int k = 0; k < nk; ++k) {
                 const int s = k % kStages;
                 if (k >= kStages)
                     mbar_wait(&empty_bar[s], ((k / kStages) - 1) & 1);
@@ -131,7 +147,7 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
     for (int i = 0; i < MM_TNB; ++i)
         acc[i] = 0.0f;
 
-    for (int k = 0; k < n_chunks; ++k) {
+    for (int k = 0; k < nk; ++k) {
         const int s = k % kStages;
         mbar_wait(&full_bar[s], (k / kStages) & 1);
         if (MM_STRESS_SKEW)
@@ -201,7 +217,7 @@ diff_sum_kernel(const unsigned char *__restrict__ cells, const unsigned char *__
 template <int DIFF>
 static cudaError_t launch(const void *cells, const void *lib, float *D, unsigned long long *best_key, int n_cell_tiles,
                           int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream, const int *cancel,
-                          unsigned long long *progress)
+                          unsigned long long *progress, Raster raster, size_t seg_stride)
 {
     const size_t smem = (size_t)kStages * kStageBytes;
     // per device (context) attribute: set on every launch, it is cheap
@@ -209,21 +225,97 @@ static cudaError_t launch(const void *cells, const void *lib, float *D, unsigned
     if (e != cudaSuccess)
         return e;
     const unsigned grid = (unsigned)n_cell_tiles * (unsigned)n_lib_tiles;  // 1-D, super-block rasterisation (kernels.h)
-    diff_sum_kernel<DIFF><<<grid, kThreads, smem, stream>>>((const unsigned char *)cells, (const unsigned char *)lib, D,
-                                                             best_key, n_chunks, n_lib, n_lib_tiles * MM_TNB, n_cells, n_cell_tiles,
-                                                             n_lib_tiles, cancel, progress);
-    return cudaGetLastError();
+    // One launch per pixel segment (split-K across LAUNCHES): the kernel itself only learns how many chunks to walk (nk) and gets
+    // its tensors pre-offset to the segment's first chunk; the tile stride inside the packed tensors stays n_chunks. Keeping the
+    // segment out of the kernel keeps its inner loop's instruction schedule exactly the one measured fastest in round 1 -- ptxas
+    // re-orders the 461-instruction loop body on the slightest change of the surrounding code, worth +-1 %.
+    for (int seg = 0; seg < raster.n_segs; ++seg) {
+        const int k0 = raster.n_segs > 1 ? seg * raster.seg_chunks : 0;
+        const int nk = raster.n_segs > 1 ? std::min(n_chunks, k0 + raster.seg_chunks) - k0 : n_chunks;
+        diff_sum_kernel<DIFF><<<grid, kThreads, smem, stream>>>(
+            (const unsigned char *)cells + (size_t)k0 * kCellBlockBytes, (const unsigned char *)lib + (size_t)k0 * kLibBlockBytes,
+            D ? D + (size_t)seg * seg_stride : nullptr, best_key, n_chunks, n_lib, n_lib_tiles * MM_TNB, n_cells, n_cell_tiles,
+            n_lib_tiles, cancel, progress, nk, raster.sb_a, raster.sb_b);
+        e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, float *D, unsigned long long *best_key,
                             int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream,
-                            const int *cancel, unsigned long long *progress)
+                            const int *cancel, unsigned long long *progress, Raster raster, size_t seg_stride)
 {
     if (n_cell_tiles <= 0 || n_lib_tiles <= 0 || n_chunks <= 0)
         return cudaSuccess;
     if (diff_type != MM_DIFF_CIEDE2000)
         return cudaErrorInvalidValue;  // RGB Euclidean / CIE76 run diff_euclid_kernel (diff_euclid.cu)
-    return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream, cancel, progress);
+    if (raster.n_segs < 1 || raster.sb_a < 1 || raster.sb_b < 1 || (raster.n_segs > 1 && (best_key || !D || raster.seg_chunks < 1)))
+        return cudaErrorInvalidValue;
+    return launch<MM_DIFF_CIEDE2000>(cells, lib, D, best_key, n_cell_tiles, n_lib_tiles, n_chunks, n_lib, n_cells, stream, cancel, progress,
+                                     raster, seg_stride);
+}
+
+// ---------------------------------------------------------------- raster choice + segment reduction
+
+Raster choose_raster(int n_cell_tiles, int n_lib_tiles, int n_chunks, bool can_split)
+{
+    auto env = [](const char *name) -> int {
+        const char *v = getenv(name);
+        return v ? atoi(v) : 0;
+    };
+    // Measured on config 4 (ncu dram__bytes_read, profiles/r2_raster_sweep.txt), segments / sb_a x sb_b -> DRAM reads, kernel time:
+    //   1 / 16 x 16: 47.4 GB, 893.8 ms     2 / 32 x 8: 30.6 GB, 894.4 ms     3 / 32 x 8: 22.5 GB, 895.2 ms     4 / 32 x 8: 22.0 GB, 895.7 ms
+    //   2 / 16 x 16: 42.8 GB               1 / 24 x 12: 102.5 GB             1 / 32 x 8: 233 GB                 2 / 64 x 4: 251 GB
+    // i.e. a hot set (sb_a cell tiles x one segment x 20 KB per chunk) of 42 MB survives in the 126 MB L2, 63 MB and more do not,
+    // and every extra launch costs ~0.6 ms of tail. Default: segments of <= 64 chunks (8,192 pixels), the widest column whose hot
+    // set stays <= 42 MB.
+    Raster r{1, n_chunks, kSuperTiles, kSuperTiles};
+    if (can_split && n_chunks > 64)
+        r.n_segs = (n_chunks + 63) / 64;
+    if (env("MM_SPLITK") > 0 && can_split)
+        r.n_segs = std::min(env("MM_SPLITK"), std::max(n_chunks, 1));
+    r.seg_chunks = (n_chunks + r.n_segs - 1) / r.n_segs;
+    r.n_segs = (n_chunks + r.seg_chunks - 1) / std::max(r.seg_chunks, 1);
+    const size_t seg_bytes = (size_t)std::max(r.seg_chunks, 1) * kCellBlockBytes;
+    int a = (int)((size_t)(42u << 20) / seg_bytes);
+    a = a >= 64 ? 64 : (a >= 32 ? 32 : 16);
+    if (env("MM_SB_A") > 0)
+        a = env("MM_SB_A");
+    r.sb_a = std::max(1, std::min(a, n_cell_tiles));
+    r.sb_b = std::max(1, 256 / r.sb_a);
+    if (env("MM_SB_B") > 0)
+        r.sb_b = env("MM_SB_B");
+    r.sb_b = std::max(1, std::min(r.sb_b, n_lib_tiles));
+    return r;
+}
+
+__global__ void sum_segments_kernel(float4 *__restrict__ D, int n_segs, size_t seg_stride4, size_t n4)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = D[i];
+        for (int s = 1; s < n_segs; ++s) {  // fixed order: the result does not depend on how the launch was scheduled
+            const float4 w = D[(size_t)s * seg_stride4 + i];
+            v.x += w.x;
+            v.y += w.y;
+            v.z += w.z;
+            v.w += w.w;
+        }
+        D[i] = v;
+    }
+}
+
+cudaError_t launch_sum_segments(float *D, int n_segs, size_t seg_stride, size_t n, cudaStream_t stream)
+{
+    if (n_segs <= 1 || n == 0)
+        return cudaSuccess;
+    if ((seg_stride | n) & 3)
+        return cudaErrorInvalidValue;  // rows are padded to the library tile (8 floats), so both are multiples of 4
+    const size_t n4 = n / 4;
+    const unsigned blocks = (unsigned)((n4 + 255) / 256 > 148 * 16 ? 148 * 16 : (n4 + 255) / 256);
+    sum_segments_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<float4 *>(D), n_segs, seg_stride / 4, n4);
+    return cudaGetLastError();
 }
 
 }  // namespace mm

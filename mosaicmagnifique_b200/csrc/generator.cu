@@ -529,8 +529,9 @@ void run_pipeline(G *g, bool candidates_only)
     // ---- Preprocess: library -> working space at the detail size of step 0 (:255-290)
     DevBuf &d_lib_work = g->ws.lib_work, &d_lib_small = g->ws.lib_small;
     int lib_ds = g->lib_size;
-    const uint8_t *lib_u8_at_ds = nullptr;
+    const uint8_t *lib_u8_at_ds = nullptr;  // 8U source of the fused packers: at lib_ds, or at lib_ds * fused_k
     bool fuse_lib_conversion = false;
+    int fused_k = 1;
     {
         const uint8_t *src = g->d_lib_u8.as<uint8_t>();
         if (g->group.detail != 1.0) {
@@ -540,6 +541,9 @@ void run_pipeline(G *g, bool candidates_only)
                 if (g->lib_stored_size != lib_ds)
                     throw Fail{MOSAIC_ERR_NOT_READY, "the library was uploaded for another detail size: call mosaic_set_library_shard "
                                                      "again after changing the cell group"};
+            } else if (n_steps == 1 && g->lib_size % lib_ds == 0) {
+                // integer ratio and a single size step: the packers below reduce on the fly, the resized 8U copy is never written
+                fused_k = g->lib_size / lib_ds;
             } else {
                 d_lib_small.alloc((size_t)N * lib_ds * lib_ds * 3, st);
                 if (g->lib_size % lib_ds == 0) {
@@ -652,10 +656,10 @@ void run_pipeline(G *g, bool candidates_only)
         d.lib_packed.alloc((size_t)n_lib_tiles * p.n_chunks * tg.lib_block, st);
         if (fuse_lib_conversion && layout == kLayoutCiede)
             CU(launch_pack_library_ciede(lib_u8_at_ds, true, d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
-                                         n_lib_tiles, g->d_lut.as<short4>(), st));
+                                         n_lib_tiles, g->d_lut.as<short4>(), st, ds * fused_k, fused_k));
         else if (fuse_lib_conversion)
-            CU(launch_pack_library_euclid_u8(lib_u8_at_ds, is_lab, d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active,
-                                             p.n_chunks, n_lib_tiles, g->d_lut.as<short4>(), st));
+            CU(launch_pack_library_euclid_u8(lib_u8_at_ds, ds * fused_k, fused_k, is_lab, d.lib_packed.p, N, P, d.pix_list.as<int>(),
+                                             p.n_active, p.n_chunks, n_lib_tiles, g->d_lut.as<short4>(), st));
         else
             CU(launch_pack_library(d_lib_work.as<float>(), d.lib_packed.p, N, P, d.pix_list.as<int>(), p.n_active, p.n_chunks,
                                    n_lib_tiles, layout, st));
@@ -711,8 +715,13 @@ void run_pipeline(G *g, bool candidates_only)
         const bool fused_argmin = !penalise && V == 1 && !candidates_only && g->world == 1 && !g->report_margins;
         const bool need_D = !fused_argmin || g->keep_D;
         DevBuf &D = g->d_D[s];
+        // CIEDE2000 launches that write D split the pixel axis into segments for L2 locality (kernels.h: Raster); the partial
+        // matrices sit seg_stride floats apart and are added in a fixed order right after the launch
+        const Raster raster = layout == kLayoutCiede ? choose_raster(n_cell_tiles, n_lib_tiles, p.n_chunks, need_D && !fused_argmin)
+                                                      : Raster{1, p.n_chunks, kSuperTiles, kSuperTiles};
+        const size_t seg_stride = (size_t)std::max(n_rows_pad, 1) * n_lib_pad;
         if (need_D) {
-            D.alloc((size_t)std::max(n_rows_pad, 1) * n_lib_pad * sizeof(float), st);
+            D.alloc(seg_stride * raster.n_segs * sizeof(float), st);
             g->have_D[s] = true;
         }
         if (fused_argmin) {
@@ -726,13 +735,17 @@ void run_pipeline(G *g, bool candidates_only)
         if (layout == kLayoutCiede)
             CU(launch_diff_sum(MM_DIFF_CIEDE2000, d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
                                fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
-                               (int)N, n_rows_local, st, g->d_cancel, d_tiles_done));
+                               (int)N, n_rows_local, st, g->d_cancel, d_tiles_done, raster, seg_stride));
         else
             CU(launch_diff_euclid(d.cells_packed.p, d.lib_packed.p, need_D ? D.as<float>() : nullptr,
                                   fused_argmin ? d.best_key.as<unsigned long long>() : nullptr, n_cell_tiles, n_lib_tiles, p.n_chunks,
                                   (int)N, n_rows_local, st, g->d_cancel, d_tiles_done));
         if (n_cell_tiles > 0)
+            tm.kernel_launches += layout == kLayoutCiede ? raster.n_segs : 1;
+        if (raster.n_segs > 1 && n_cell_tiles > 0) {
+            CU(launch_sum_segments(D.as<float>(), raster.n_segs, seg_stride, seg_stride, st));
             tm.kernel_launches++;
+        }
         clock.end();
         const int step_weight = (int)pow(4.0, (double)(n_steps - 1 - s));
         const int positions = p.rows * p.cols;
@@ -741,7 +754,7 @@ void run_pipeline(G *g, bool candidates_only)
             cudaEvent_t done;
             CU(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
             cudaEventRecord(done, st);
-            const unsigned long long total = (unsigned long long)std::max(n_cell_tiles, 1) * (unsigned long long)n_lib_tiles;
+            const unsigned long long total = (unsigned long long)std::max(n_cell_tiles, 1) * (unsigned long long)n_lib_tiles * raster.n_segs;
             int last = progress;
             while (cudaEventQuery(done) == cudaErrorNotReady) {
                 if (cudaMemcpyAsync(g->h_progress, d_tiles_done, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g->poll_stream) == cudaSuccess &&

@@ -39,12 +39,23 @@
 
 namespace mm {
 
-// CTA rasterisation shared by both difference kernels: a 1-D grid walks the (cell tile, library tile) plane in
-// super-blocks of kSuperTiles x kSuperTiles tiles (cell tile fastest inside a super-block, super-blocks along the cell
-// axis first). The ~256 CTAs of a super-block are co-resident and stream their pixel chunks roughly in step, so each
-// cell chunk is fetched from HBM once per 16 library tiles and each library chunk once per 16 cell tiles (L2 serves the
-// rest); the plain (cell fastest over ALL cell tiles) order re-read the whole cell tensor for every library tile:
-// 842 GB of DRAM reads for config 4 instead of ~95 GB (profiles/r1_diff_sum_ciede2000_final_cfg4.txt).
+// CTA rasterisation of the CIEDE2000 kernel: a 1-D grid walks the (cell tile, library tile) plane of one pixel segment in
+// super-blocks of sb_a cell tiles x sb_b library tiles (cell tile fastest inside a super-block), so that the ~296 co-resident
+// CTAs (2 per SM) form one super-block and stream its chunks roughly in step:
+//   * inside a super-block every library chunk is fetched from HBM once for sb_a CTAs and every cell chunk once for sb_b CTAs
+//     (L2 serves the rest);
+//   * consecutive super-blocks keep the SAME column of sb_a cell tiles and move along the library axis, so the column's cell
+//     chunks (sb_a x seg_chunks x 20 KB) stay hot in the 126 MB L2 for the whole sweep: the library is streamed from HBM once per
+//     cell column, the cells once.
+// Config 4 history (ncu dram__bytes_read): plain order 842 GB; round 1 (16 x 16 super-blocks, library band kept, whole cells per
+// CTA) 124-132 GB = 40 x the 3.3 GB the launch needs; cell column kept instead 47.4 GB; plus two pixel segments of 64 chunks
+// (one launch each, partial sums added in a fixed order by sum_segments_kernel) and 32 x 8 super-blocks 30.6 GB, four segments
+// 22.0 GB (profiles/r2_raster_sweep.txt).
+struct Raster {
+    int n_segs;      // pixel segments = launches (split-K); 1 = whole cells per CTA
+    int seg_chunks;  // chunks per segment
+    int sb_a, sb_b;  // super-block: cell tiles x library tiles
+};
 constexpr int kSuperTiles = 16;
 #if defined(__CUDACC__)
 // strong system-scope load of the cancel word: it is written by the copy engine while the kernel runs, so it must come from L2
@@ -55,6 +66,8 @@ __device__ __forceinline__ int load_cancel_flag(const int *p)
     asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Euclidean kernel: 16 x 16 super-blocks, a band of library tiles kept (cell tile fastest inside a super-block, super-blocks along
+// the cell axis first) -- round 1's order; its operand traffic per pixel pair is 10 x smaller than the CIEDE2000 kernel's
 __device__ __forceinline__ void tile_of_block(unsigned id, int n_ct, int n_lt, int &cell_tile, int &lib_tile)
 {
     const unsigned band_ctas = (unsigned)n_ct * kSuperTiles;  // CTAs of one full band of kSuperTiles library tiles
@@ -90,11 +103,19 @@ inline TileGeom tile_geom(PackLayout l)
 cudaError_t launch_diff_euclid(const void *cells, const void *lib, float *D, unsigned long long *best_key, int n_cell_tiles,
                                int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream,
                                const int *cancel = nullptr, unsigned long long *progress = nullptr);
+// Raster of a CIEDE2000 launch (see above): segments only when the partial sums have somewhere to go (D is written) and the cells
+// are long enough to be worth splitting. MM_SPLITK / MM_SB_A / MM_SB_B in the environment override the choice (tuning).
+Raster choose_raster(int n_cell_tiles, int n_lib_tiles, int n_chunks, bool can_split);
+// D[0][i] += D[1][i] + ... + D[n_segs-1][i] (fixed order); seg_stride in floats
+cudaError_t launch_sum_segments(float *D, int n_segs, size_t seg_stride, size_t n, cudaStream_t stream);
 
 // ---- diff_kernels.cu
+// raster.n_segs > 1: one launch per pixel segment, D holds n_segs partial matrices seg_stride floats apart (add them with
+// launch_sum_segments); best_key must then be null (the fused argmin needs complete sums)
 cudaError_t launch_diff_sum(int diff_type, const void *cells, const void *lib, float *D, unsigned long long *best_key,
                             int n_cell_tiles, int n_lib_tiles, int n_chunks, int n_lib, int n_cells, cudaStream_t stream,
-                            const int *cancel = nullptr, unsigned long long *progress = nullptr);
+                            const int *cancel = nullptr, unsigned long long *progress = nullptr,
+                            Raster raster = Raster{1, 0, kSuperTiles, kSuperTiles}, size_t seg_stride = 0);
 
 // ---- prep_kernels.cu
 // u8 BGR -> working space f32 AoS [pixel][3]: Lab through the OpenCV-compatible LUT (is_lab) or a plain cast.
@@ -140,13 +161,16 @@ cudaError_t launch_pack_library(const float *lib, void *packed, int64_t n, int P
 
 // CIEDE2000 layout straight from the 8U BGR library at the detail size (Lab conversion fused, no f32 intermediate) or from
 // the f32 working-space library; padding slots are written by the same pass
+// src_is_u8: src_size x src_size images reduced k-fold on the fly (8U INTER_AREA, integer ratio; src_size 0 = already P pixels)
 cudaError_t launch_pack_library_ciede(const void *src, bool src_is_u8, void *packed, int64_t n, int P, const int *pix_list,
-                                      int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream);
+                                      int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream,
+                                      int src_size = 0, int k = 1);
 
-// Euclidean layout straight from the 8U BGR library at the detail size (plain cast, or the Lab conversion for CIE76, fused);
-// padding slots are written by the same pass
-cudaError_t launch_pack_library_euclid_u8(const uint8_t *lib, bool is_lab, void *packed, int64_t n, int P, const int *pix_list,
-                                          int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream);
+// Euclidean layout straight from the 8U BGR library (src_size x src_size images, reduced k-fold on the fly by the 8U INTER_AREA
+// arithmetic; plain cast, or the Lab conversion for CIE76, fused); padding slots are written by the same pass
+cudaError_t launch_pack_library_euclid_u8(const uint8_t *lib, int src_size, int k, bool is_lab, void *packed, int64_t n, int P,
+                                          const int *pix_list, int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut,
+                                          cudaStream_t stream);
 
 struct CellDesc {
     int x0, y0;          // top-left of the (unclipped) cell rect in main-image space

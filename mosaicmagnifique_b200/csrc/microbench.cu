@@ -140,6 +140,51 @@ __global__ void __launch_bounds__(256) mixed_kernel(float *out, float a, float b
         *clk = t1 - t0;
 }
 
+// packed and scalar FP32 in one loop: N2 fma.rn.f32x2 + N1 scalar fma per iteration on independent chains. If scalar FFMA could
+// issue to a second FP32 pipe while FFMA2 holds the first, the combined lane-op rate would exceed either pure rate.
+template <int N2, int N1>
+__global__ void __launch_bounds__(256) mix_f2_f1_kernel(float *out, float a, float b, long long *clk)
+{
+    unsigned long long x[N2];
+    float y[N1];
+    unsigned long long av, bv;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(av) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bv) : "f"(b));
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+        const float lo = (float)(threadIdx.x + i), hi = lo + 0.5f;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(x[i]) : "f"(lo), "f"(hi));
+    }
+#pragma unroll
+    for (int i = 0; i < N1; ++i)
+        y[i] = (float)(threadIdx.x + 3 * i);
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < kIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < (N2 > N1 ? N2 : N1); ++i) {
+            if (i < N2)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x[i]) : "l"(av), "l"(bv));
+            if (i < N1)
+                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(y[i]) : "f"(a), "f"(b));
+        }
+    }
+    const long long t1 = clock64();
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < N2; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x[i]));
+        s += lo + hi;
+    }
+#pragma unroll
+    for (int i = 0; i < N1; ++i)
+        s += y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *clk = t1 - t0;
+}
+
 cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream)
 {
     if (n_out < 6)
@@ -202,6 +247,26 @@ cudaError_t run_microbench(double *out, int n_out, cudaStream_t stream)
         }
     }
     out[4] = (double)sms;
+    // [9], [10]: FP32 lane-ops/s of 8 FFMA2 + 8 FFMA and of 8 FFMA2 + 16 FFMA per iteration
+    for (int which = 0; which < 2 && n_out >= 11; ++which) {
+        float best_ms = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            cudaEventRecord(e0, stream);
+            if (which == 0)
+                mix_f2_f1_kernel<8, 8><<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk);
+            else
+                mix_f2_f1_kernel<8, 16><<<blocks, threads, 0, stream>>>(buf, 1.0001f, 0.5f, clk);
+            cudaEventRecord(e1, stream);
+            e = cudaEventSynchronize(e1);
+            if (e != cudaSuccess)
+                goto done;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep > 0 && ms < best_ms)
+                best_ms = ms;
+        }
+        out[9 + which] = (double)blocks * threads * kIters * (which == 0 ? 24.0 : 32.0) / (best_ms * 1e-3);
+    }
 
 done:
     cudaEventDestroy(e0);

@@ -196,6 +196,33 @@ cudaError_t launch_area_u8(const uint8_t *src, uint8_t *dst, int64_t n, int src_
     return cudaGetLastError();
 }
 
+// One output pixel of the same 8U INTER_AREA (integer ratio k) straight from the source image: what the fused library packers read
+// when the resize to the detail size has not been materialised (k == 1: the pixel itself)
+__device__ __forceinline__ void area_pixel_u8(const uint8_t *__restrict__ img, int S, int k, int py, int px, int out[3])
+{
+    const uint8_t *s = img + ((size_t)(py * k) * S + (size_t)px * k) * 3;
+    if (k == 1) {
+        out[0] = s[0];
+        out[1] = s[1];
+        out[2] = s[2];
+        return;
+    }
+    int sum[3] = {0, 0, 0};
+    for (int yy = 0; yy < k; ++yy)
+        for (int xx = 0; xx < k; ++xx) {
+            const uint8_t *t = s + ((size_t)yy * S + xx) * 3;
+            sum[0] += t[0];
+            sum[1] += t[1];
+            sum[2] += t[2];
+        }
+    const float scale = 1.0f / (float)(k * k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int v = (k == 2) ? (sum[c] + 2) >> 2 : __float2int_rn(__fmul_rn((float)sum[c], scale));
+        out[c] = min(max(v, 0), 255);
+    }
+}
+
 // sum of a k x k block in OpenCV's order: groups of four taps (row-major inside the block) are added
 // left to right and each group total is added to the running sum; the remainder tap by tap.
 template <typename F>
@@ -388,7 +415,7 @@ __global__ void pack_library_euclid_kernel(const float *__restrict__ lib, unsign
 constexpr int kEuclidRow = 3 * MM_ETN + 1;  // padded pixel stride of the staging tile (bank spread of the transposing writes)
 template <bool kLab>
 __global__ void __launch_bounds__(256)
-pack_library_euclid_u8_kernel(const uint8_t *__restrict__ lib, unsigned char *__restrict__ packed, int64_t n, int P,
+pack_library_euclid_u8_kernel(const uint8_t *__restrict__ lib, int S, int k, unsigned char *__restrict__ packed, int64_t n, int P,
                               const int *__restrict__ pix_list, int n_active, int n_chunks, size_t n_blocks,
                               const short4 *__restrict__ lut)
 {
@@ -402,13 +429,15 @@ pack_library_euclid_u8_kernel(const uint8_t *__restrict__ lib, unsigned char *__
             const int64_t im = (int64_t)tile * MM_ETN + ti;
             float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f;
             if (q < n_active && im < n) {
-                const uint8_t *s8 = lib + ((size_t)im * P + pix_list[q]) * 3;
+                const int ds = S / k, p = pix_list[q];
+                int c8[3];
+                area_pixel_u8(lib + (size_t)im * S * S * 3, S, k, p / ds, p % ds, c8);
                 if (kLab) {
-                    lab_from_bgr8(s8[0], s8[1], s8[2], lut, v0, v1, v2);
+                    lab_from_bgr8((unsigned char)c8[0], (unsigned char)c8[1], (unsigned char)c8[2], lut, v0, v1, v2);
                 } else {
-                    v0 = (float)s8[0];
-                    v1 = (float)s8[1];
-                    v2 = (float)s8[2];
+                    v0 = (float)c8[0];
+                    v1 = (float)c8[1];
+                    v2 = (float)c8[2];
                 }
             }
             float *d = s + pi * kEuclidRow + ti;  // library values are stored NEGATED (cell - lib becomes a packed add)
@@ -424,19 +453,22 @@ pack_library_euclid_u8_kernel(const uint8_t *__restrict__ lib, unsigned char *__
     }
 }
 
-cudaError_t launch_pack_library_euclid_u8(const uint8_t *lib, bool is_lab, void *packed, int64_t n, int P, const int *pix_list,
-                                          int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream)
+cudaError_t launch_pack_library_euclid_u8(const uint8_t *lib, int src_size, int k, bool is_lab, void *packed, int64_t n, int P,
+                                          const int *pix_list, int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut,
+                                          cudaStream_t stream)
 {
+    if (k < 1 || src_size % k != 0 || (src_size / k) * (src_size / k) != P)
+        return cudaErrorInvalidValue;
     const size_t n_blocks = (size_t)n_lib_tiles * n_chunks;
     if (n_blocks == 0)
         return cudaSuccess;
     const int grid = (int)(n_blocks < 148 * 16 ? n_blocks : 148 * 16);
     if (is_lab)
-        pack_library_euclid_u8_kernel<true><<<grid, 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active, n_chunks,
-                                                                      n_blocks, lab_lut);
+        pack_library_euclid_u8_kernel<true><<<grid, 256, 0, stream>>>(lib, src_size, k, (unsigned char *)packed, n, P, pix_list, n_active,
+                                                                      n_chunks, n_blocks, lab_lut);
     else
-        pack_library_euclid_u8_kernel<false><<<grid, 256, 0, stream>>>(lib, (unsigned char *)packed, n, P, pix_list, n_active, n_chunks,
-                                                                       n_blocks, lab_lut);
+        pack_library_euclid_u8_kernel<false><<<grid, 256, 0, stream>>>(lib, src_size, k, (unsigned char *)packed, n, P, pix_list, n_active,
+                                                                       n_chunks, n_blocks, lab_lut);
     return cudaGetLastError();
 }
 
@@ -447,7 +479,7 @@ cudaError_t launch_pack_library_euclid_u8(const uint8_t *lib, bool is_lab, void 
 // library (1.97 GB written and read again at config 4) is never materialised. Used when there is a single size step;
 // with size steps the f32 copy is needed for the per-step halving (CPUPhotomosaicGenerator.cpp:95-99).
 template <bool kFromU8>
-__global__ void pack_library_ciede_kernel(const void *__restrict__ src, unsigned char *__restrict__ packed, int64_t n, int P,
+__global__ void pack_library_ciede_kernel(const void *__restrict__ src, int S, int k, unsigned char *__restrict__ packed, int64_t n, int P,
                                           const int *__restrict__ pix_list, int n_active, int n_chunks, int64_t n_pair_slots,
                                           const short4 *__restrict__ lut)
 {
@@ -466,8 +498,11 @@ __global__ void pack_library_ciede_kernel(const void *__restrict__ src, unsigned
                     continue;
                 float L, a, b;
                 if (kFromU8) {
-                    const uint8_t *s8 = reinterpret_cast<const uint8_t *>(src) + ((size_t)im * P + px) * 3;
-                    lab_from_bgr8(s8[0], s8[1], s8[2], lut, L, a, b);
+                    // S x S source, reduced k-fold on the fly (8U INTER_AREA as area_u8_kernel computes it; k == 1: a plain read)
+                    const int ds = S / k;
+                    int c8[3];
+                    area_pixel_u8(reinterpret_cast<const uint8_t *>(src) + (size_t)im * S * S * 3, S, k, px / ds, px % ds, c8);
+                    lab_from_bgr8((unsigned char)c8[0], (unsigned char)c8[1], (unsigned char)c8[2], lut, L, a, b);
                 } else {
                     const float *sf = reinterpret_cast<const float *>(src) + ((size_t)im * P + px) * 3;
                     L = sf[0];
@@ -487,18 +522,27 @@ __global__ void pack_library_ciede_kernel(const void *__restrict__ src, unsigned
 }
 
 cudaError_t launch_pack_library_ciede(const void *src, bool src_is_u8, void *packed, int64_t n, int P, const int *pix_list,
-                                      int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream)
+                                      int n_active, int n_chunks, int n_lib_tiles, const short4 *lab_lut, cudaStream_t stream,
+                                      int src_size, int k)
 {
+    if (src_is_u8 && src_size == 0) {  // source already at the detail size
+        src_size = 1;
+        while (src_size * src_size < P)
+            ++src_size;
+        k = 1;
+    }
+    if (src_is_u8 && (k < 1 || src_size % k != 0 || (src_size / k) * (src_size / k) != P))
+        return cudaErrorInvalidValue;
     const int64_t n_pair_slots = (int64_t)n_lib_tiles * (MM_TNB / 2);
     const size_t total = (size_t)n_pair_slots * n_chunks * MM_KP;
     if (total == 0)
         return cudaSuccess;
     if (src_is_u8)
-        pack_library_ciede_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(src, (unsigned char *)packed, n, P, pix_list, n_active,
-                                                                                  n_chunks, n_pair_slots, lab_lut);
+        pack_library_ciede_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(src, src_size, k, (unsigned char *)packed, n, P, pix_list,
+                                                                                  n_active, n_chunks, n_pair_slots, lab_lut);
     else
-        pack_library_ciede_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(src, (unsigned char *)packed, n, P, pix_list, n_active,
-                                                                                   n_chunks, n_pair_slots, lab_lut);
+        pack_library_ciede_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(src, 0, 1, (unsigned char *)packed, n, P, pix_list,
+                                                                                   n_active, n_chunks, n_pair_slots, lab_lut);
     return cudaGetLastError();
 }
 

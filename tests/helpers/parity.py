@@ -10,8 +10,15 @@ import numpy as np
 # (measured error of whole sums: <= 5e-7). Two candidates' sums can therefore be mis-ordered only if the f64
 # sums differ by less than 2 x 4.9e-6 ~ 1e-5 relative: that is the tie band. (Round 1 used 1e-4, 200 x the measured error.)
 TIE_TOL = 1e-5
-# Difference values: BASELINE.json asks for 1e-4 relative; the tests hold the engine to 2e-5.
-D_TOL = 2e-5
+# Difference values: BASELINE.json asks for 1e-4 relative, and that is the bound on EVERY sum (D_TOL). FP32 rounding and the
+# polynomial pieces stay far below it (median error of config-4 sums 5e-8, 99 % of all sums of every test below D_TOL_TYPICAL);
+# the sums that reach 1e-5 .. 7e-5 contain a pixel pair with EXACTLY opposite hues -- OpenCV's Lab values are multiples of 1/64,
+# so e.g. (a, b) = (40.25, -20.125) against (-35.90625, 17.953125) does occur in uniform noise. There the reference formula is
+# discontinuous (mean hue +- 180 deg, ColourDifference.cpp:109-122: 58.18 or 72.89 for that pair), the reference lands on one side
+# by the last bit of its two f64 atan2 results, the engine by a fixed rule (documented deviation). One such
+# pixel in a clipped 4,608-pixel edge cell is the measured worst case, 6.6e-5.
+D_TOL = 1e-4
+D_TOL_TYPICAL = 2e-6
 
 
 def window_counts(grid, x, y, rng_, n_lib):
@@ -53,3 +60,12 @@ def check_grid(D_oracle, grid_state, gpu_grid, repeat_range, repeat_addition, to
 
 def rel_err(D_gpu, D_oracle):
     return np.abs(D_gpu.astype(np.float64) - D_oracle) / np.maximum(np.abs(D_oracle), 1e-6)
+
+
+def check_differences(D_gpu, D_oracle):
+    """every sum within the spec's 1e-4, 99 % of them within what FP32 explains; returns the relative errors"""
+    e = rel_err(D_gpu, D_oracle)
+    if e.size:
+        assert e.max() < D_TOL, "max relative error of the difference sums %.3g" % e.max()
+        assert np.quantile(e, 0.99) < D_TOL_TYPICAL, "99th percentile of the relative errors %.3g" % np.quantile(e, 0.99)
+    return e

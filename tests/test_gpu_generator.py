@@ -1,14 +1,14 @@
 """End-to-end parity of the generator on the GPU against the CPU oracle, through the reference-shaped API.
 Option matrix follows the reference's generator tests (test/tst_Generator.h:145-439, tst_CUDAGenerator.h:226-823):
 {RGB, CIE76, CIEDE2000} x {detail 100, 50}, repeats, size steps, a non-square cell shape with flips, edge cells.
-Criterion: grid equality outside the tie band (helpers/parity.py: 1e-5 relative, what FP32 can explain), difference sums within
-2e-5 relative (BASELINE.json asks for 1e-4)."""
+Criterion: grid equality outside the tie band (helpers/parity.py: 1e-5 relative), every difference sum within BASELINE.json's
+1e-4 relative and 99 % of them within 2e-6 (helpers/parity.py explains the outliers)."""
 import os
 
 import numpy as np
 import pytest
 
-from tests.helpers.parity import D_TOL, TIE_TOL, check_grid, rel_err
+from tests.helpers.parity import D_TOL, TIE_TOL, check_differences, check_grid, rel_err
 
 pytestmark = pytest.mark.gpu
 TOL = TIE_TOL  # grid criterion: a cell may differ only if its two candidates are within the FP32-explainable band (1e-5)
@@ -67,9 +67,7 @@ def _run_case(oracle, main, lib, o_shape, diff, detail, steps, rr, ra, use_oracl
     for step, (g, w) in enumerate(zip(got, want)):
         D = gen.getDifferences(step)
         assert D.shape == w.D.shape
-        if D.size:
-            e = rel_err(D, w.D)
-            assert e.max() < D_TOL, "step %d: max relative error of the difference sums %.3g" % (step, e.max())
+        check_differences(D, w.D)
         n, t, bad = check_grid(w.D, states[step], g, rr, ra, TOL)
         assert not bad, "step %d: %d cells differ outside the tie band, first %s" % (step, len(bad), bad[:3])
         total += n
@@ -96,6 +94,38 @@ def test_square_cells(oracle, diff, detail):
 def test_no_repeats_fused_argmin(oracle):
     main, lib = _inputs(21, 160, 160, 45, 32)
     _run_case(oracle, main, lib, oracle.CellShape.square(32), 2, 100, 0, 0, 0)
+
+
+@pytest.mark.parametrize("splitk,sb_a,sb_b", [(None, None, None), (3, 8, 4), (7, 64, 1), (1, 2, 300)])
+def test_split_pixel_segments_and_super_block_shapes(oracle, monkeypatch, splitk, sb_a, sb_b):
+    """CIEDE2000 launches that write D split the pixel axis into segments (partial sums added in a fixed order) and walk the tile
+    plane in super-blocks (kernels.h: Raster). 128 px cells at detail 100 % = 128 chunks: the default plan (4 segments of 32) and
+    forced odd plans -- 3 and 7 segments that do not divide 128, super-blocks wider / taller than the grid -- all against the
+    f64 oracle, and two runs of one plan bit-identical."""
+    for name, v in (("MM_SPLITK", splitk), ("MM_SB_A", sb_a), ("MM_SB_B", sb_b)):
+        if v is None:
+            monkeypatch.delenv(name, raising=False)
+        else:
+            monkeypatch.setenv(name, str(v))
+    main, lib = _inputs(23, 420, 560, 37, 128)
+    _run_case(oracle, main, lib, oracle.CellShape.square(128), 2, 100, 0, 2, 300)
+    from mosaicmagnifique_b200 import CellGroup, CellShape, PhotomosaicGenerator
+    gen = PhotomosaicGenerator(0)
+    gen.setMainImage(main)
+    gen.setLibrary(lib)
+    gen.setColourDifference(2)
+    cg = CellGroup()
+    cg.setCellShape(CellShape(128))
+    gen.setCellGroup(cg)
+    gen.computeGridState()
+    gen.setRepeat(2, 300)
+    gen.setKeepDifferences(True)
+    runs = []
+    for _ in range(2):
+        assert gen.generateBestFits()
+        runs.append(gen.getDifferences(0).copy())
+    gen.close()
+    assert np.array_equal(runs[0].view(np.uint32), runs[1].view(np.uint32))
 
 
 def test_hexagon_like_shape_with_flips_and_edges(oracle):
@@ -248,7 +278,7 @@ def test_build_photomosaic(oracle, hexa, steps, detail):
 @pytest.mark.parametrize("name", ["square_ciede2000", "triangle_rgb", "hexagon_cie76"])
 def test_generator_matches_committed_golden(oracle, name):
     """The CUDA path against the COMMITTED fixtures of tests/golden/generator_golden.npz (inputs and oracle outputs written
-    by tests/golden/make_generator_golden.py in the build container): difference sums within 2e-5 relative, grid states
+    by tests/golden/make_generator_golden.py in the build container): difference sums within 1e-4 relative (99 % within 2e-6), grid states
     identical, grids identical outside the tie band. No oracle run is involved, only its recorded numbers."""
     from mosaicmagnifique_b200 import CellGroup, PhotomosaicGenerator
     from tests.test_oracle_pipeline import _golden, golden_case
@@ -275,8 +305,7 @@ def test_generator_matches_committed_golden(oracle, name):
         D_want = G["%s/D%d" % (name, s)]
         D = gen.getDifferences(s)
         assert D.shape == D_want.shape
-        if D.size:
-            assert rel_err(D, D_want).max() < D_TOL
+        check_differences(D, D_want)
         n, ties, bad = check_grid(D_want, states[s], got[s], rr, ra, TOL)
         assert not bad, bad[:3]
         # outside the tie band the recorded oracle grid is reproduced exactly
