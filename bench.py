@@ -48,7 +48,8 @@ WORK_REFERENCE_FORMULA = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1},
 # dram__bytes_read.sum + dram__bytes_write.sum of the difference kernel, per launch on 1 GPU, from the ncu --set full captures
 # committed under profiles/ (not measurable inside an un-profiled run): workload -> (bytes, file)
 NCU_TRAFFIC = {
-    "cfg4": (132214958000 + 197510656, "profiles/r1_diff_sum_ciede2000_v4_cfg4.txt"),
+    # both pixel-segment launches of the default plan (2 segments, 32 x 8 super-blocks): 15.8 + 14.8 GB read, 0.28 GB written
+    "cfg4": (30600000000 + 280000000, "profiles/r2_raster_sweep.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum; round 1: 132.4 GB)"),
 }
 
 WORKLOADS = {
@@ -591,7 +592,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a collective that does not complete within 3 minutes is a bug, not a slow step: fail fast instead of holding 8 GPUs
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
@@ -618,10 +621,12 @@ def main():
         for name in SECONDARY:
             c2 = WORKLOADS[name]
             r2 = B200Run(name, c2, rank, world, local_rank)
-            # short steps after a long idle phase (input generation on the CPU): warm up for >= 0.5 s so that the clocks are up
+            # short steps after a long idle phase (input generation on the CPU): warm up for >= 0.5 s so that the clocks are up.
+            # The number of warm-up steps comes from a timing, so it is agreed on by ALL ranks (max over ranks) -- every step is a
+            # collective under torchrun, and ranks that disagree on the count dead-lock.
             t_w = time.perf_counter()
             r2.step()
-            one = max(time.perf_counter() - t_w, 1e-3)
+            (one,) = r2.allmax([max(time.perf_counter() - t_w, 1e-3)])
             m2 = r2.measure(min(args.steps, 5), max(3, min(50, int(0.5 / one))), 2, sample_clocks=True)
             m2["valid_cells"] = r2.valid_cells
             s2 = summarise(name, c2, m2, world, roofline_of(name, c2, m2, mb, peaks, sass, world))
