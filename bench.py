@@ -593,8 +593,8 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         import datetime
-        # a collective that does not complete within 3 minutes is a bug, not a slow step: fail fast instead of holding 8 GPUs
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
+        # a collective that does not complete within 5 minutes is a bug, not a slow step: fail fast instead of holding 8 GPUs
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
