@@ -11,8 +11,9 @@ produces per iteration (stated per kernel below) to give the executed work per p
     packed FP32 (FFMA2 / FMUL2 / FADD2)  : 2 FP32 lane-ops each, FMA-heavy pipe, 2 issue cycles
     scalar FP32 (FFMA / FMUL / FADD ...) : 1 lane-op
     MUFU.*                               : XU pipe (16 lanes / clk / SM)
-bench.py reads profiles/r2_sass_counts.json (committed; regenerate after every kernel change -- the file records the size and
-mtime-independent SHA-256 of the library it was taken from, and bench.py reports whether that still matches).
+bench.py reads profiles/r2_sass_counts.json (committed; regenerate after every kernel change) and, where cuobjdump is available,
+re-derives the counts from the library it actually loaded and reports whether they agree (the build is not byte-reproducible, so
+counts are compared, not file hashes).
 """
 import hashlib
 import json
@@ -88,11 +89,13 @@ def classify(body):
     return c, ops
 
 
-def main():
-    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
+def analyse(lib=LIB, write_listings=False):
+    """Counts of the hot loops of `lib`. The build is not byte-reproducible (nvcc embeds unique ids), so consumers compare COUNTS,
+    not file hashes: bench.py re-runs this on the library it loaded and checks it against the committed JSON."""
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
     funcs = functions(sass)
-    sha = hashlib.sha256(open(LIB, "rb").read()).hexdigest()
-    result = {"library": os.path.relpath(LIB, ROOT), "library_sha256": sha, "arch": "sm_100a" if "sm_100a" in sass else "?", "kernels": {}}
+    sha = hashlib.sha256(open(lib, "rb").read()).hexdigest()
+    result = {"library": os.path.relpath(lib, ROOT), "library_sha256": sha, "arch": "sm_100a" if "sm_100a" in sass else "?", "kernels": {}}
     whole = {}
     for instrs in funcs.values():
         for _, t in instrs:
@@ -123,6 +126,8 @@ def main():
              "tma_mbarrier_in_function": {op: sum(1 for _, t in instrs if re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0] == op)
                                           for op in ("UBLKCP", "SYNCS")}}
         result["kernels"][short] = k
+        if not write_listings:
+            continue
         path = os.path.join(ROOT, "profiles", "r2_sass_%s.txt" % short)
         with open(path, "w") as f:
             f.write("# cuobjdump -sass %s  -- function %s\n" % (result["library"], fn))
@@ -137,6 +142,11 @@ def main():
                 mark = "L " if lo <= a <= hi else "  "
                 f.write("%s/*%04x*/ %s ;\n" % (mark, a, t))
         print("%s: loop %s..%s  %s  per pixel-diff %s" % (short, hex(lo), hex(hi), c, k["per_pixel_diff"]))
+    return result
+
+
+def main():
+    result = analyse(LIB, write_listings=True)
     with open(os.path.join(ROOT, "profiles", "r2_sass_counts.json"), "w") as f:
         json.dump(result, f, indent=1)
         f.write("\n")
