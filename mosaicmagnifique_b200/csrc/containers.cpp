@@ -404,30 +404,281 @@ void png_encode(const Image8 &img, std::vector<uint8_t> &out)
     ihdr.push_back(0);
     ihdr.push_back(0);
     chunk("IHDR", ihdr);
-    // scanlines: filter byte 0 + samples in PNG order (RGB / RGBA)
+    // scanlines in PNG sample order (RGB / RGBA), each with the filter (None / Sub / Up / Average / Paeth) that minimises the sum
+    // of absolute signed residuals -- libpng's default heuristic
     const size_t row = (size_t)img.cols * img.channels;
+    const int bpp = img.channels;
+    std::vector<uint8_t> cur(row), prev(row, 0), cand(row), best(row);
     std::vector<uint8_t> raw;
     raw.reserve((row + 1) * img.rows);
     for (int y = 0; y < img.rows; ++y) {
-        raw.push_back(0);
         const uint8_t *s = &img.px[(size_t)y * row];
         for (int x = 0; x < img.cols; ++x)
             for (int c = 0; c < img.channels; ++c)
-                raw.push_back(s[(size_t)x * img.channels + (img.channels >= 3 && c < 3 ? 2 - c : c)]);
+                cur[(size_t)x * img.channels + c] = s[(size_t)x * img.channels + (img.channels >= 3 && c < 3 ? 2 - c : c)];
+        int best_f = 0;
+        uint64_t best_cost = ~0ull;
+        for (int f = 0; f < 5; ++f) {
+            uint64_t cost = 0;
+            for (size_t i = 0; i < row; ++i) {
+                const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= (size_t)bpp ? prev[i - bpp] : 0;
+                int pred = 0;
+                if (f == 1)
+                    pred = a;
+                else if (f == 2)
+                    pred = b;
+                else if (f == 3)
+                    pred = (a + b) >> 1;
+                else if (f == 4) {
+                    const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c);
+                    pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                }
+                const uint8_t r = (uint8_t)(cur[i] - pred);
+                cand[i] = r;
+                cost += r < 128 ? r : 256 - r;
+            }
+            if (cost < best_cost) {
+                best_cost = cost;
+                best_f = f;
+                best.swap(cand);
+            }
+        }
+        raw.push_back((uint8_t)best_f);
+        raw.insert(raw.end(), best.begin(), best.end());
+        prev = cur;
     }
-    // zlib stream of stored blocks
-    std::vector<uint8_t> z = {0x78, 0x01};
-    size_t pos = 0;
-    do {
-        const size_t len = std::min<size_t>(65535, raw.size() - pos);
-        z.push_back(pos + len >= raw.size() ? 1 : 0);
-        z.push_back((uint8_t)(len & 255));
-        z.push_back((uint8_t)(len >> 8));
-        z.push_back((uint8_t)(~len & 255));
-        z.push_back((uint8_t)((~len >> 8) & 255));
-        z.insert(z.end(), raw.begin() + pos, raw.begin() + pos + len);
-        pos += len;
-    } while (pos < raw.size());
+    // zlib stream: one deflate block (RFC 1951) -- LZ77 over a 32 KB window with hash chains, then whichever of the fixed and a
+    // dynamic Huffman coding of the token stream is shorter (masks: long matches, either is tiny; photographs: almost only literal
+    // filter residuals, which only a dynamic code shortens)
+    std::vector<uint8_t> z = {0x78, 0x5E};
+    {
+        static const int len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+        static const int len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+        static const int dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+        static const int dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+        struct Token {
+            uint16_t len;   // 0 = literal
+            uint16_t dist;  // literal value when len == 0
+        };
+        // ---- LZ77
+        std::vector<Token> tokens;
+        const size_t n = raw.size();
+        tokens.reserve(n / 2 + 16);
+        constexpr int kHashBits = 15, kWindow = 32768, kMaxChain = 48;
+        std::vector<int32_t> head((size_t)1 << kHashBits, -1), chain(n, -1);
+        auto hash3 = [&](size_t i) { return ((raw[i] << 10) ^ (raw[i + 1] << 5) ^ raw[i + 2]) & ((1 << kHashBits) - 1); };
+        for (size_t i = 0; i < n;) {
+            int best_len = 0, best_dist = 0;
+            if (i + 3 <= n) {
+                int32_t cand_pos = head[hash3(i)];
+                for (int tries = 0; cand_pos >= 0 && (i - (size_t)cand_pos) <= (size_t)kWindow && tries < kMaxChain; ++tries) {
+                    const size_t max_len = std::min<size_t>(258, n - i);
+                    size_t l = 0;
+                    while (l < max_len && raw[cand_pos + l] == raw[i + l])
+                        ++l;
+                    if ((int)l > best_len) {
+                        best_len = (int)l;
+                        best_dist = (int)(i - (size_t)cand_pos);
+                        if (l == max_len)
+                            break;
+                    }
+                    cand_pos = chain[cand_pos];
+                }
+            }
+            const size_t step = best_len >= 3 ? (size_t)best_len : 1;
+            tokens.push_back(best_len >= 3 ? Token{(uint16_t)best_len, (uint16_t)best_dist} : Token{0, raw[i]});
+            for (size_t k = i; k < i + step; ++k)  // enter the covered positions into the hash chains
+                if (k + 3 <= n) {
+                    const int h = hash3(k);
+                    chain[k] = head[h];
+                    head[h] = (int32_t)k;
+                }
+            i += step;
+        }
+        auto len_code = [&](int len) {
+            int c = 28;
+            while (len_base[c] > len)
+                --c;
+            return c;
+        };
+        auto dist_code = [&](int dist) {
+            int c = 29;
+            while (dist_base[c] > dist)
+                --c;
+            return c;
+        };
+        // ---- code lengths: fixed, and dynamic (Huffman on the token statistics, limited to 15 bits the way miniz does it)
+        std::vector<uint32_t> f_ll(286, 0), f_d(30, 0);
+        for (const Token &t : tokens)
+            if (t.len) {
+                f_ll[257 + len_code(t.len)]++;
+                f_d[dist_code(t.dist)]++;
+            } else
+                f_ll[t.dist]++;
+        f_ll[256] = 1;
+        auto huff_lengths = [](const std::vector<uint32_t> &freq, int max_bits) {
+            const int m = (int)freq.size();
+            std::vector<uint8_t> len(m, 0);
+            std::vector<int> used;
+            for (int i = 0; i < m; ++i)
+                if (freq[i])
+                    used.push_back(i);
+            if (used.empty())
+                return len;
+            if (used.size() == 1) {
+                len[used[0]] = 1;
+                return len;
+            }
+            // plain Huffman tree by repeated merging (m <= 286: quadratic selection is fine)
+            struct Node {
+                uint64_t w;
+                int l, r;
+            };
+            std::vector<Node> nodes;
+            std::vector<int> live;
+            for (int i : used) {
+                nodes.push_back(Node{freq[i], -1, -1});
+                live.push_back((int)nodes.size() - 1);
+            }
+            while (live.size() > 1) {
+                std::sort(live.begin(), live.end(), [&](int a, int b) { return nodes[a].w > nodes[b].w || (nodes[a].w == nodes[b].w && a < b); });
+                const int a = live.back();
+                live.pop_back();
+                const int b = live.back();
+                live.pop_back();
+                nodes.push_back(Node{nodes[a].w + nodes[b].w, a, b});
+                live.push_back((int)nodes.size() - 1);
+            }
+            std::vector<int> depth(nodes.size(), 0), stack = {live[0]};
+            std::vector<int> num(64, 0);
+            while (!stack.empty()) {
+                const int v = stack.back();
+                stack.pop_back();
+                if (nodes[v].l < 0) {
+                    num[std::min(depth[v], 63)]++;
+                    continue;
+                }
+                depth[nodes[v].l] = depth[nodes[v].r] = depth[v] + 1;
+                stack.push_back(nodes[v].l);
+                stack.push_back(nodes[v].r);
+            }
+            // limit to max_bits: fold the deeper leaves into max_bits and repair the Kraft sum (miniz: enforce_max_code_size)
+            for (int i = max_bits + 1; i < 64; ++i) {
+                num[max_bits] += num[i];
+                num[i] = 0;
+            }
+            uint64_t total = 0;
+            for (int i = max_bits; i > 0; --i)
+                total += (uint64_t)num[i] << (max_bits - i);
+            while (total != (1ull << max_bits)) {
+                num[max_bits]--;
+                for (int i = max_bits - 1; i > 0; --i)
+                    if (num[i]) {
+                        num[i]--;
+                        num[i + 1] += 2;
+                        break;
+                    }
+                total--;
+            }
+            // hand the lengths out: most frequent symbols get the shortest codes
+            std::sort(used.begin(), used.end(), [&](int a, int b) { return freq[a] > freq[b] || (freq[a] == freq[b] && a < b); });
+            size_t k = 0;
+            for (int bits = 1; bits <= max_bits; ++bits)
+                for (int c = 0; c < num[bits]; ++c)
+                    len[used[k++]] = (uint8_t)bits;
+            return len;
+        };
+        auto canonical = [](const std::vector<uint8_t> &len) {
+            std::vector<uint16_t> code(len.size(), 0);
+            int bl_count[16] = {0}, next[16] = {0};
+            for (uint8_t l : len)
+                bl_count[l]++;
+            bl_count[0] = 0;
+            int c = 0;
+            for (int b = 1; b < 16; ++b) {
+                c = (c + bl_count[b - 1]) << 1;
+                next[b] = c;
+            }
+            for (size_t i = 0; i < len.size(); ++i)
+                if (len[i])
+                    code[i] = (uint16_t)next[len[i]]++;
+            return code;
+        };
+        std::vector<uint8_t> fix_ll(288), fix_d(30, 5);
+        for (int i = 0; i < 288; ++i)
+            fix_ll[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+        std::vector<uint8_t> dyn_ll = huff_lengths(f_ll, 15), dyn_d = huff_lengths(f_d, 15);
+        if (std::count(dyn_d.begin(), dyn_d.end(), 0) == (long)dyn_d.size())
+            dyn_d[0] = 1;  // at least one distance code must be described
+        auto body_bits = [&](const std::vector<uint8_t> &ll, const std::vector<uint8_t> &d) {
+            uint64_t bits = ll[256];
+            for (int i = 0; i < 286; ++i)
+                bits += (uint64_t)f_ll[i] * ll[i] + (i >= 257 ? (uint64_t)f_ll[i] * len_extra[i - 257] : 0);
+            bits -= ll[256];  // (f_ll[256] == 1 is already in the loop)
+            for (int i = 0; i < 30; ++i)
+                bits += (uint64_t)f_d[i] * (d[i] + dist_extra[i]);
+            return bits;
+        };
+        // dynamic header, code lengths sent without run-length symbols: 5 + 5 + 4 + 19 * 3 + (286 + 30) code-length codes
+        std::vector<uint32_t> f_cl(19, 0);
+        for (int i = 0; i < 286; ++i)
+            f_cl[dyn_ll[i]]++;
+        for (int i = 0; i < 30; ++i)
+            f_cl[dyn_d[i]]++;
+        const std::vector<uint8_t> cl_len = huff_lengths(f_cl, 7);
+        uint64_t hdr_bits = 14 + 19 * 3;
+        for (int i = 0; i < 19; ++i)
+            hdr_bits += (uint64_t)f_cl[i] * cl_len[i];
+        const bool use_dynamic = hdr_bits + body_bits(dyn_ll, dyn_d) < body_bits(fix_ll, fix_d);
+        const std::vector<uint8_t> &ll_len = use_dynamic ? dyn_ll : fix_ll, &d_len = use_dynamic ? dyn_d : fix_d;
+        const std::vector<uint16_t> ll_code = canonical(ll_len), d_code = canonical(d_len), cl_code = canonical(cl_len);
+        // ---- bit stream
+        uint64_t acc = 0;
+        int nbits = 0;
+        auto put = [&](uint32_t v, int nb) {  // nb bits, LSB first
+            acc |= (uint64_t)v << nbits;
+            nbits += nb;
+            while (nbits >= 8) {
+                z.push_back((uint8_t)(acc & 255));
+                acc >>= 8;
+                nbits -= 8;
+            }
+        };
+        auto put_code = [&](uint32_t code, int nb) {  // Huffman codes go out MSB first
+            uint32_t r = 0;
+            for (int i = 0; i < nb; ++i)
+                r |= ((code >> i) & 1u) << (nb - 1 - i);
+            put(r, nb);
+        };
+        put(1, 1);                     // BFINAL
+        put(use_dynamic ? 2 : 1, 2);   // BTYPE
+        if (use_dynamic) {
+            static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+            put(286 - 257, 5);
+            put(30 - 1, 5);
+            put(19 - 4, 4);
+            for (int i = 0; i < 19; ++i)
+                put(cl_len[order[i]], 3);
+            for (int i = 0; i < 286; ++i)
+                put_code(cl_code[dyn_ll[i]], cl_len[dyn_ll[i]]);
+            for (int i = 0; i < 30; ++i)
+                put_code(cl_code[dyn_d[i]], cl_len[dyn_d[i]]);
+        }
+        for (const Token &t : tokens) {
+            if (!t.len) {
+                put_code(ll_code[t.dist], ll_len[t.dist]);
+                continue;
+            }
+            const int lc = len_code(t.len), dc = dist_code(t.dist);
+            put_code(ll_code[257 + lc], ll_len[257 + lc]);
+            put((uint32_t)(t.len - len_base[lc]), len_extra[lc]);
+            put_code(d_code[dc], d_len[dc]);
+            put((uint32_t)(t.dist - dist_base[dc]), dist_extra[dc]);
+        }
+        put_code(ll_code[256], ll_len[256]);  // end of block
+        if (nbits > 0)
+            put(0, 8 - nbits);
+    }
     put_be32(z, adler32_of(raw.data(), raw.size()));
     chunk("IDAT", z);
     chunk("IEND", {});
