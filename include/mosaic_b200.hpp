@@ -297,8 +297,34 @@ public:
         ck(mosaic_build_photomosaic(m_g, backgroundBGRA, outBGRA, rows, cols, step));
     }
     int getMaxProgress() { return mosaic_get_max_progress(m_g); }
+    // slot cancel(): callable from any thread or from inside the progress callback; the running kernel drains within milliseconds
+    // and generateBestFits() returns false. Sticky like the reference's m_wasCanceled until resetCancel().
     void cancel() { mosaic_cancel(m_g); }
+    void resetCancel() { mosaic_reset_cancel(m_g); }
+    // signal progress(int): fn is called on the generating thread with the reference's cumulative values
+    // (grid positions done, weighted 4^(steps - 1 - step), CPUPhotomosaicGenerator.cpp:55, 87-88)
     void setProgressCallback(mosaic_progress_fn fn, void *user) { mosaic_set_progress_callback(m_g, fn, user); }
+
+    // ---- one generator per GPU of a multi-GPU run (no reference counterpart; see mosaic_b200.h "multi-GPU sharding"):
+    // setShard + generateCandidates on every rank, one all-gather of candidateBlock() in rank order, selectFromGathered on every rank
+    void setShard(int rank, int world) { ck(mosaic_set_shard(m_g, rank, world)); }
+    void generateCandidates() { ck(mosaic_generate_candidates(m_g)); }
+    struct CandidateBlock {
+        void *device = nullptr;   // {float scores [rowsPerRank][k], int32 indices [rowsPerRank][k]}
+        int64_t rowsPerRank = 0;
+        int k = 0;
+        size_t bytes = 0;
+    };
+    CandidateBlock candidateBlock(int step) const
+    {
+        CandidateBlock b;
+        mosaic_get_candidate_block(m_g, step, &b.device, &b.rowsPerRank, &b.k, &b.bytes);
+        return b;
+    }
+    void selectFromGathered(int step, const void *gatheredBlocks, int k, int64_t rowsPerRank)
+    {
+        ck(mosaic_select_from_gathered(m_g, step, gatheredBlocks, k, rowsPerRank));
+    }
     std::string lastError() const { return mosaic_last_error(m_g); }
     mosaic_timings timings() const
     {
