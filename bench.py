@@ -50,6 +50,7 @@ WORK_REFERENCE_FORMULA = {2: {"flop": 110, "sfu": 27}, 0: {"flop": 9, "sfu": 1},
 NCU_TRAFFIC = {
     # both pixel-segment launches of the default plan (2 segments, 32 x 8 super-blocks): 15.8 + 14.8 GB read, 0.28 GB written
     "cfg4": (30600000000 + 280000000, "profiles/r2_raster_sweep.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum; round 1: 132.4 GB)"),
+    "cfg5": (32300478000 + 15758592, "profiles/r2_diff_euclid_cfg5.txt (ncu --set full at full size; algorithmic 1.28 GB)"),
 }
 
 WORKLOADS = {
