@@ -139,6 +139,10 @@ int mosaic_get_timings(const mosaic_generator *g, mosaic_timings *out);
  * (score, index) candidates per cell; the caller all-gathers them (NCCL) and every rank runs the
  * order-dependent selection on the gathered candidates. */
 int mosaic_set_shard(mosaic_generator *g, int rank, int world);
+/* the split mosaic_set_shard implies for a step with n_valid_cells valid cells (host arithmetic, no device needed): rank r owns the
+ * cells [first_cell, first_cell + n_cells) of the raster order and rows_per_rank rows of the all-gathered candidate buffer */
+int mosaic_host_shard_split(int64_t n_valid_cells, int colour_difference, int rank, int world, int64_t *rows_per_rank, int64_t *first_cell,
+                            int64_t *n_cells);
 /* preprocessing + difference sums + top-K for this rank's cells of every step */
 int mosaic_generate_candidates(mosaic_generator *g);
 int mosaic_get_candidate_count(const mosaic_generator *g, int step, int64_t *first_cell, int64_t *n_cells, int *k);

@@ -78,6 +78,7 @@ def capi():
         "mosaic_get_margins": (i, [vp, i, vp, vp, i64]),
         "mosaic_get_timings": (i, [vp, c.POINTER(Timings)]),
         "mosaic_set_shard": (i, [vp, i, i]),
+        "mosaic_host_shard_split": (i, [i64, i, i, i, i64p, i64p, i64p]),
         "mosaic_generate_candidates": (i, [vp]),
         "mosaic_get_candidate_count": (i, [vp, i, i64p, i64p, ip]),
         "mosaic_get_candidates_device": (i, [vp, i, c.POINTER(vp), c.POINTER(vp)]),

@@ -356,6 +356,17 @@ void check_ready(G *g)
                    "library images must be at the cell size (the reference resizes them before setLibrary, MainWindow.cpp:575-581)"};
 }
 
+// the shard split of one size step: rank r of `world` owns rows [begin, end) of the n valid cells (raster order); every rank owns
+// per_rank rows of the padded list, a whole number of cell tiles of the colour difference's kernel
+void shard_split(int64_t n, int diff_type, int rank, int world, int64_t &per_rank, int64_t &begin, int64_t &end)
+{
+    const int tcb = tile_geom(diff_type == MOSAIC_CIEDE2000 ? kLayoutCiede : kLayoutEuclid).tcb;
+    const int64_t n_tiles = (n + tcb - 1) / tcb;
+    per_rank = std::max<int64_t>(1, (n_tiles + world - 1) / world) * tcb;
+    begin = std::min<int64_t>(n, (int64_t)rank * per_rank);
+    end = std::min<int64_t>(n, (int64_t)(rank + 1) * per_rank);
+}
+
 void make_plans(G *g)
 {
     const Group &grp = g->group;
@@ -407,12 +418,7 @@ void make_plans(G *g)
         // rank's block of cells: a contiguous raster range of the step's valid cells, cut at cell granularity on whole cell
         // tiles. Every rank owns the same number of rows `per` of the padded list (the last ranks may own fewer real cells), so
         // that rank r's candidates land at row r * per of one all-gathered buffer without any size exchange.
-        const int64_t n = (int64_t)p.cell_pos.size();
-        const int tcb = tile_geom(g->diff_type == MOSAIC_CIEDE2000 ? kLayoutCiede : kLayoutEuclid).tcb;
-        const int64_t n_tiles = (n + tcb - 1) / tcb;
-        p.per_rank = std::max<int64_t>(1, (n_tiles + g->world - 1) / g->world) * tcb;
-        p.cell_begin = std::min<int64_t>(n, (int64_t)g->rank * p.per_rank);
-        p.cell_end = std::min<int64_t>(n, (int64_t)(g->rank + 1) * p.per_rank);
+        shard_split((int64_t)p.cell_pos.size(), g->diff_type, g->rank, g->world, p.per_rank, p.cell_begin, p.cell_end);
     }
 }
 
@@ -1494,6 +1500,22 @@ int mosaic_set_shard(mosaic_generator *g, int rank, int world)
         return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setShard: need 0 <= rank < world");
     g->rank = rank;
     g->world = world;
+    return MOSAIC_OK;
+}
+
+int mosaic_host_shard_split(int64_t n_valid_cells, int colour_difference, int rank, int world, int64_t *rows_per_rank, int64_t *first_cell,
+                            int64_t *n_cells)
+{
+    if (n_valid_cells < 0 || colour_difference < 0 || colour_difference > 2 || world < 1 || rank < 0 || rank >= world)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    int64_t per = 0, b = 0, e = 0;
+    shard_split(n_valid_cells, colour_difference, rank, world, per, b, e);
+    if (rows_per_rank)
+        *rows_per_rank = per;
+    if (first_cell)
+        *first_cell = b;
+    if (n_cells)
+        *n_cells = e - b;
     return MOSAIC_OK;
 }
 

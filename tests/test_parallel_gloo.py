@@ -70,3 +70,23 @@ def test_split_rows(n_valid, world, tile):
         pos += c
     # balanced to one tile: no rank owns more than ceil(tiles / world) tiles
     assert per == max(1, -(-(-(-n_valid // tile)) // world)) * tile
+
+
+def test_split_rows_is_the_engines_split():
+    """parallel.split_rows (what the Python side assumes about the gathered buffer) against the engine's own arithmetic
+    (generator.cu::shard_split through mosaic_host_shard_split), for both kernels' cell tiles."""
+    import ctypes
+
+    from mosaicmagnifique_b200 import capi
+    from mosaicmagnifique_b200.parallel import split_rows
+    L = capi()
+    rng = np.random.default_rng(8)
+    cases = [(2040, 8), (11664, 8), (1999, 8), (5, 8), (0, 3), (64, 2), (65, 2), (13823, 4)] + [(int(rng.integers(0, 30000)), int(rng.integers(1, 17))) for _ in range(200)]
+    for n_valid, world in cases:
+        for diff, tile in ((2, 8), (0, 64), (1, 64)):
+            per, parts = split_rows(n_valid, world, tile)
+            for r in range(world):
+                p, f, c = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+                assert L.mosaic_host_shard_split(n_valid, diff, r, world, ctypes.byref(p), ctypes.byref(f), ctypes.byref(c)) == 0
+                assert (p.value, f.value, c.value) == (per, parts[r][0], parts[r][1]), (n_valid, world, diff, r)
+    assert L.mosaic_host_shard_split(10, 2, 3, 3, None, None, None) == -1
