@@ -1,9 +1,23 @@
 """Debug / analysis: how much work an EXACT prune of the difference sums could save on config-4-shaped data.
-CIE76 stands in for CIEDE2000 (same data, same geometry); rows of a 128 px cell play the part of the 128-pixel chunks."""
+Rows of a 128 px cell play the part of the 128-pixel chunks. Default metric: CIE76 (numpy, fast); `--ciede` evaluates the real
+CIEDE2000 per pixel with the f64 oracle (test infrastructure; ~15 s of CPU per cell)."""
 import numpy as np, cv2, time, sys
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from mosaicmagnifique_b200 import synthetic
 N=10000; S=128; K=145
+CIEDE = "--ciede" in sys.argv
+if CIEDE:
+    from oracle import oracle
+    oracle.build()
+def cell_rows(cell):
+    """[N][S] row sums of the per-pixel difference between `cell` and every library image"""
+    if not CIEDE:
+        return np.sqrt(((libL-cell[None])**2).sum(-1)).sum(2)
+    out=np.empty((N,S))
+    c=np.ascontiguousarray(np.broadcast_to(cell[None],(250,S,S,3))).reshape(-1,3)
+    for i in range(0,N,250):
+        out[i:i+250]=oracle.diff_batch(2,c,libL[i:i+250].reshape(-1,3)).reshape(250,S,S).sum(2)
+    return out
 lib=synthetic.make_library(N,S,1004)
 main=synthetic.make_main_image(4320,7680,2004)
 t=time.time()
@@ -26,8 +40,7 @@ rng=np.random.default_rng(0)
 res=[]
 for (cy,cx) in [(3,5),(10,20),(20,40),(30,55),(15,33),(8,48)]:
     cell=mainL[cy*S:(cy+1)*S,cx*S:(cx+1)*S]
-    d=np.sqrt(((libL-cell[None])**2).sum(-1))   # N,S,S   CIE76 stand-in
-    rows=d.sum(2)                                # N,S row sums
+    rows=cell_rows(cell)                         # N,S row sums
     pre=np.cumsum(rows,1)                        # prefix over rows (each row = 1 chunk of 128 px)
     full=pre[:,-1]
     T=np.sort(full)[K-1]
@@ -61,7 +74,7 @@ for S_ in (4, 8, 16):
     fr=[]
     for (cy,cx) in [(3,5),(10,20),(20,40),(30,55),(15,33),(8,48)]:
         cell=mainL[cy*S:(cy+1)*S,cx*S:(cx+1)*S]
-        d=np.sqrt(((libL-cell[None])**2).sum(-1)); rows=d.sum(2); pre=np.cumsum(rows,1); full=pre[:,-1]
+        rows=cell_rows(cell); pre=np.cumsum(rows,1); full=pre[:,-1]
         seg=S//S_
         R=[pre[:,(s+1)*seg-1] for s in range(S_)]          # running totals after each segment
         M=int(1.25*K)+8
