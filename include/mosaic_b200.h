@@ -91,6 +91,12 @@ int mosaic_set_colour_scheme(mosaic_generator *g, int type);     /* setColourSch
  * differs from shape->size the shape is first resized like CellShape::resized (CellShape.cpp:281-312). */
 int mosaic_set_cell_group(mosaic_generator *g, const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size,
                           int detail_percent, int size_steps);
+/* The same for a shape that came from CellShape::loadFromFile (mosaic_mcs_load): with mask_as_stored != 0 the mask is taken as the
+ * file holds it -- loadFromFile does not threshold (CellShape.cpp:405-410), non-zero = active everywhere downstream
+ * (CPUPhotomosaicGenerator.cpp:150), and only RESIZED masks are binarised (CellShape::resized -> setCellMask). Identical to
+ * mosaic_set_cell_group for the binary masks the reference itself writes. */
+int mosaic_set_cell_group_ex(mosaic_generator *g, const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size,
+                             int detail_percent, int size_steps, int mask_as_stored);
 /* getCellGroup(): geometry of the normal (detail = 0) or detail (detail = 1) cell of one step */
 int mosaic_get_cell_shape(const mosaic_generator *g, int step, int detail, mosaic_cell_shape *out, uint8_t *mask_out,
                           size_t mask_capacity);
@@ -226,6 +232,11 @@ int mosaic_kernel_microbench(int device, double *out, int n_out);
 void mosaic_grid_size(const mosaic_cell_shape *shape, int image_w, int image_h, int pad, int *grid_w, int *grid_h);
 void mosaic_rect_at(const mosaic_cell_shape *shape, int x, int y, int rect_xywh[4]);
 int mosaic_flip_at(const mosaic_cell_shape *shape, int x, int y); /* flip_h + 2 * flip_v */
+/* CellGroup::getCell(step, detail) (CellShape/CellGroup.cpp:65-145) of the group mosaic_set_cell_group[_ex] would build, computed on
+ * the host without a generator handle (what the CPU tests compare with the reference's own CellGroup.cpp object code) */
+int mosaic_host_cell_group_cell(const mosaic_cell_shape *shape, const uint8_t *mask, int mask_as_stored, int cell_size,
+                                int detail_percent, int size_steps, int step, int detail, mosaic_cell_shape *out, uint8_t *mask_out,
+                                size_t mask_capacity);
 /* GridGenerator::getGridState (Grid/GridGenerator.cpp:29-193) with the reference's HOST arithmetic (the generator object
  * evaluates the same rule on the GPU, mosaic_compute_grid_state). Steps are written back to back into out:
  * step s holds step_rows[s] x step_cols[s] values, -1 = nullopt, 0 = valid. bgr may be NULL (no entropy rule). */

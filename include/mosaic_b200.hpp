@@ -75,9 +75,12 @@ public:
         if (mosaic_mcs_load(filename.c_str(), &c, mask.data(), mask.size(), nullptr, 0) != MOSAIC_OK)
             throw std::invalid_argument(mosaic_io_last_error());
         m_mask = std::move(mask);  // as stored: loadFromFile does not threshold (CellShape.cpp:405-410)
+        m_asStored = true;
         m_c = c;
         m_name = name;
     }
+    // true for a shape that came from loadFromFile: its mask is kept as the file holds it (non-zero = active downstream)
+    bool maskAsStored() const { return m_asStored; }
     void saveToFile(const std::string &filename) const
     {
         if (mosaic_mcs_save(filename.c_str(), &m_c, m_mask.data(), m_name.c_str()) != MOSAIC_OK)
@@ -94,6 +97,7 @@ private:
     std::vector<uint8_t> m_mask;
     mosaic_cell_shape m_c{};
     std::string m_name;
+    bool m_asStored = false;
 };
 
 class CellGroup {
@@ -250,8 +254,8 @@ public:
     void setCellGroup(const CellGroup &cg)
     {
         m_cells = cg;
-        ck(mosaic_set_cell_group(m_g, &cg.getCellShape().c(), cg.getCellShape().getCellMask().data(), 0, cg.getDetailPercent(),
-                                 static_cast<int>(cg.getSizeSteps())));
+        ck(mosaic_set_cell_group_ex(m_g, &cg.getCellShape().c(), cg.getCellShape().getCellMask().data(), 0, cg.getDetailPercent(),
+                                    static_cast<int>(cg.getSizeSteps()), cg.getCellShape().maskAsStored() ? 1 : 0));
     }
     CellGroup &getCellGroup() { return m_cells; }
     void setGridState(const GridUtility::MosaicBestFit &state)

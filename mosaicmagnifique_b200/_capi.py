@@ -57,6 +57,8 @@ def capi():
         "mosaic_set_colour_difference": (i, [vp, i]),
         "mosaic_set_colour_scheme": (i, [vp, i]),
         "mosaic_set_cell_group": (i, [vp, shp, vp, i, i, i]),
+        "mosaic_set_cell_group_ex": (i, [vp, shp, vp, i, i, i, i]),
+        "mosaic_host_cell_group_cell": (i, [shp, vp, i, i, i, i, i, i, shp, vp, sz]),
         "mosaic_get_cell_shape": (i, [vp, i, i, shp, vp, sz]),
         "mosaic_set_grid_state": (i, [vp, i, i, i, vp]),
         "mosaic_compute_grid_state": (i, [vp]),

@@ -208,9 +208,12 @@ int guard(G *g, const char *what, void (*fn)(G *, void *), void *arg)
     }
 }
 
-void shape_from_c(const mosaic_cell_shape &c, const uint8_t *mask, Shape &s)
+void shape_from_c(const mosaic_cell_shape &c, const uint8_t *mask, Shape &s, bool mask_as_stored = false)
 {
-    s.set_mask(mask, c.size);
+    if (mask_as_stored)
+        s.set_mask_as_stored(mask, c.size);
+    else
+        s.set_mask(mask, c.size);
     s.row_spacing = c.row_spacing;
     s.col_spacing = c.col_spacing;
     s.alt_row_spacing = c.alt_row_spacing;
@@ -1135,13 +1138,19 @@ int mosaic_set_variant_quirk(mosaic_generator *g, int faithful)
 int mosaic_set_cell_group(mosaic_generator *g, const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size, int detail_percent,
                           int size_steps)
 {
+    return mosaic_set_cell_group_ex(g, shape, mask, cell_size, detail_percent, size_steps, 0);
+}
+
+int mosaic_set_cell_group_ex(mosaic_generator *g, const mosaic_cell_shape *shape, const uint8_t *mask, int cell_size, int detail_percent,
+                             int size_steps, int mask_as_stored)
+{
     if (!g)
         return MOSAIC_ERR_INVALID_ARGUMENT;
     if (!shape || !mask || shape->size <= 0)
         return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setCellGroup: missing shape or mask");
     try {
         Shape top;
-        shape_from_c(*shape, mask, top);
+        shape_from_c(*shape, mask, top, mask_as_stored != 0);
         std::string err;
         if (cell_size > 0 && cell_size != top.size) {
             Shape r;
@@ -1160,6 +1169,39 @@ int mosaic_set_cell_group(mosaic_generator *g, const mosaic_cell_shape *shape, c
         return g->fail(MOSAIC_ERR_OUT_OF_MEMORY, "setCellGroup: host allocation failed");
     } catch (...) {
         return g->fail(MOSAIC_ERR_INVALID_ARGUMENT, "setCellGroup: unexpected failure");
+    }
+}
+
+int mosaic_host_cell_group_cell(const mosaic_cell_shape *shape, const uint8_t *mask, int mask_as_stored, int cell_size, int detail_percent,
+                                int size_steps, int step, int detail, mosaic_cell_shape *out, uint8_t *mask_out, size_t mask_capacity)
+{
+    if (!shape || !mask || !out || shape->size <= 0 || step < 0 || step > size_steps)
+        return MOSAIC_ERR_INVALID_ARGUMENT;
+    try {
+        Shape top;
+        shape_from_c(*shape, mask, top, mask_as_stored != 0);
+        std::string err;
+        if (cell_size > 0 && cell_size != top.size) {
+            Shape r;
+            if (!top.resized(cell_size, r, err))
+                return MOSAIC_ERR_UNSUPPORTED;
+            top = r;
+        }
+        Group grp;
+        if (!grp.build(top, detail_percent, size_steps, err))
+            return MOSAIC_ERR_INVALID_ARGUMENT;
+        const Shape &s = detail ? grp.detail_cells[step] : grp.cells[step];
+        shape_to_c(s, *out);
+        if (mask_out) {
+            if (mask_capacity < s.mask.size())
+                return MOSAIC_ERR_INVALID_ARGUMENT;
+            memcpy(mask_out, s.mask.data(), s.mask.size());
+        }
+        return MOSAIC_OK;
+    } catch (const std::bad_alloc &) {
+        return MOSAIC_ERR_OUT_OF_MEMORY;
+    } catch (...) {
+        return MOSAIC_ERR_INVALID_ARGUMENT;
     }
 }
 

@@ -215,6 +215,12 @@ void Shape::set_mask(const uint8_t *m, int s)
         mask[i] = m[i] > 127 ? 255 : 0;
 }
 
+void Shape::set_mask_as_stored(const uint8_t *m, int s)
+{
+    size = s;
+    mask.assign(m, m + (size_t)s * s);
+}
+
 std::vector<uint8_t> Shape::masks4() const
 {
     std::vector<uint8_t> out((size_t)4 * size * size);

@@ -17,7 +17,7 @@ namespace mm {
 constexpr int kPadGrid = 2;  // GridUtility::PAD_GRID, GridUtility.h:33
 
 struct Shape {
-    std::vector<uint8_t> mask;  // size x size, 0 / 255
+    std::vector<uint8_t> mask;  // size x size; non-zero = active (0 / 255 unless the shape was loaded from a file with grey values)
     int size = 0;
     int row_spacing = 0, col_spacing = 0, alt_row_spacing = 0, alt_col_spacing = 0;
     int alt_row_offset = 0, alt_col_offset = 0;
@@ -26,6 +26,9 @@ struct Shape {
     bool empty() const { return size == 0; }
     // setCellMask: THRESH_BINARY at 127 (CellShape.cpp:116-135)
     void set_mask(const uint8_t *m, int s);
+    // CellShape::loadFromFile keeps the decoded mask as stored (CellShape.cpp:405-410): no threshold. Every later test is
+    // `mask != 0` (CPUPhotomosaicGenerator.cpp:150), and resized() thresholds the RESIZED mask, not this one
+    void set_mask_as_stored(const uint8_t *m, int s);
     // the four flipped masks, index = flip_h + 2 * flip_v (CellShape::getCellMask, CellShape.cpp:138-152)
     std::vector<uint8_t> masks4() const;
     // CellShape::resized (CellShape.cpp:281-312); false + err when the resize is not supported

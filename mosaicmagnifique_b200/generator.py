@@ -45,14 +45,17 @@ PAD_GRID = 2  # GridUtility::PAD_GRID
 class CellShape:
     """CellShape (src/CellShape/CellShape.h:98-109): a binary square mask plus tiling parameters."""
 
-    def __init__(self, mask_or_size):
+    def __init__(self, mask_or_size, as_stored: bool = False):
+        """as_stored: the mask comes from CellShape::loadFromFile, which keeps the decoded values (no threshold, CellShape.cpp:405-410);
+        non-zero = active downstream, and only resized() binarises. Makes no difference for the binary masks the reference writes."""
+        self._as_stored = bool(as_stored)
         if isinstance(mask_or_size, (int, np.integer)):
             mask = np.full((int(mask_or_size), int(mask_or_size)), 255, np.uint8)  # CellShape(size_t), CellShape.cpp:66-69
         else:
             mask = np.asarray(mask_or_size)
         if mask.ndim != 2 or mask.shape[0] != mask.shape[1] or mask.dtype != np.uint8:
             raise ValueError("Unsupported mask type")  # std::invalid_argument, CellShape.cpp:133
-        self._mask = np.where(mask > 127, 255, 0).astype(np.uint8)  # setCellMask threshold
+        self._mask = np.ascontiguousarray(mask) if as_stored else np.where(mask > 127, 255, 0).astype(np.uint8)  # setCellMask threshold
         s = mask.shape[0]
         self.rowSpacing = self.colSpacing = self.alternateRowSpacing = self.alternateColSpacing = s
         self.alternateRowOffset = self.alternateColOffset = 0
@@ -78,8 +81,8 @@ class CellShape:
                           int(self.alternateRowFlipVertical))
 
     @staticmethod
-    def _from_c(c: CellShapeC, mask: np.ndarray) -> "CellShape":
-        s = CellShape(mask)
+    def _from_c(c: CellShapeC, mask: np.ndarray, as_stored: bool = False) -> "CellShape":
+        s = CellShape(mask, as_stored=as_stored)
         s.rowSpacing, s.colSpacing = c.row_spacing, c.col_spacing
         s.alternateRowSpacing, s.alternateColSpacing = c.alt_row_spacing, c.alt_col_spacing
         s.alternateRowOffset, s.alternateColOffset = c.alt_row_offset, c.alt_col_offset
@@ -109,7 +112,7 @@ class CellShape:
         return r
 
     def _copy(self):
-        r = CellShape(self._mask)
+        r = CellShape(self._mask, as_stored=self._as_stored)
         r.__dict__.update({k: v for k, v in self.__dict__.items() if k != "_mask"})
         return r
 
@@ -128,7 +131,7 @@ def load_mcs(path: str) -> CellShape:
     rc = L.mosaic_mcs_load(bpath, ctypes.byref(c), mask.ctypes.data, mask.size, name, len(name))
     if rc:
         raise MosaicError(rc, L.mosaic_io_last_error().decode())
-    s = CellShape._from_c(c, mask)
+    s = CellShape._from_c(c, mask, as_stored=True)
     s.name = name.value.decode()
     return s
 
@@ -244,7 +247,8 @@ class PhotomosaicGenerator:
             raise ValueError("cell group has no shape")
         c = cells._shape._c()
         m = cells._shape.getCellMask()
-        self._ck(self._L.mosaic_set_cell_group(self._h, ctypes.byref(c), m.ctypes.data, 0, cells._detail, cells._size_steps))
+        self._ck(self._L.mosaic_set_cell_group_ex(self._h, ctypes.byref(c), m.ctypes.data, 0, cells._detail, cells._size_steps,
+                                                  int(cells._shape._as_stored)))
         self._cells = cells
 
     def getCellGroup(self) -> CellGroup:

@@ -684,6 +684,11 @@ def _ref():
         R.ref_cell_group_cell.argtypes = [vp, vp, i, i, i, i, vp, vp, lng]
         R.ref_cell_shape_resized.argtypes = [vp, vp, i, vp, vp, lng]
         R.ref_mcs_load.argtypes = [ctypes.c_char_p, vp, vp, lng, ctypes.c_char_p, i]
+        if hasattr(R, "ref_mcs_group_cell"):  # (absent from a library prebuilt before round 2)
+            R.ref_mcs_group_cell.argtypes = [ctypes.c_char_p, i, i, i, i, i, vp, vp, lng]
+        if hasattr(R, "ref_cancel_after"):
+            R.ref_cancel_after.argtypes = [i]
+            R.ref_progress_get.argtypes = [vp, i]
         R.ref_mcs_save.argtypes = [ctypes.c_char_p, vp, vp, ctypes.c_char_p]
         R.ref_library_create.restype = vp
         R.ref_library_create.argtypes = [i]
@@ -866,6 +871,16 @@ def reference_load_mcs(path: str):
     if rc < 0:
         raise RuntimeError("reference loadFromFile failed")
     return _shape_from(params, masks, name.value.decode())
+
+
+def reference_mcs_group_cell(path: str, cell_size: int, detail_percent: int, size_steps: int, step: int, detail: bool):
+    """loadFromFile -> [resized(cell_size)] -> CellGroup -> getCell(step, detail), all by the reference's own object code."""
+    params, masks = _describe_out(2048)
+    rc = _ref().ref_mcs_group_cell(path.encode(), int(cell_size), int(detail_percent), int(size_steps), int(step), int(detail),
+                                   params.ctypes.data, masks.ctypes.data, masks.size)
+    if rc < 0:
+        raise RuntimeError("reference CellGroup from .mcs failed (%d)" % rc)
+    return _shape_from(params, masks)
 
 
 def reference_save_mcs(path: str, shape: CellShape, name: str = ""):

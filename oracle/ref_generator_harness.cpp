@@ -328,6 +328,26 @@ int ref_mcs_load(const char *path, int *params, unsigned char *mask4, long mask_
         return -3;
     }
 }
+// What the application does with a shape file (MainWindow: loadFromFile, then the cell-size spin box -> resized, then the CellGroup):
+// the normal / detail cell of one size step. cell_size <= 0 keeps the stored size. Returns the cell size, -1 / -3 as ref_mcs_load.
+int ref_mcs_group_cell(const char *path, int cell_size, int detail_percent, int size_steps, int step, int detail, int *params,
+                       unsigned char *mask4, long mask_capacity)
+{
+    try {
+        CellShape c;
+        c.loadFromFile(QString(path));
+        CellGroup g;
+        g.setCellShape(cell_size > 0 ? c.resized(cell_size) : c);
+        g.setDetail(detail_percent);
+        g.setSizeSteps(static_cast<size_t>(size_steps));
+        describe(g.getCell((size_t)step, detail != 0), params, mask4, mask_capacity);
+        return params[0];
+    } catch (const std::invalid_argument &) {
+        return -1;
+    } catch (const std::exception &) {
+        return -3;
+    }
+}
 // CellShape::saveToFile (CellShape.cpp:321-360)
 int ref_mcs_save(const char *path, const int *shape, const unsigned char *mask, const char *name_utf8)
 {
